@@ -1,0 +1,159 @@
+/*
+ * oc_b200.h -- C ABI of the B200-native batched Overcooked environment step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference (LukavdBoogaard/JAXOvercooked,
+ * 100 % Python on JAX) has no FFI of its own; its de-facto interface is the object protocol
+ *
+ *     obs, state                        = env.reset(key)                  overcooked.py:136
+ *     obs, state, rewards, dones, infos = env.step(key, state, actions)   multi_agent_env.py:41-69
+ *     obs                               = env.get_obs(state)              overcooked.py:250
+ *
+ * called under jax.vmap over N environments (baselines/IPPO_CL.py:478, :538).  Each entry point below is
+ * what an XLA FFI custom call (or the ctypes host in jaxovercooked_b200/) binds for one of those calls,
+ * batched over the leading N; see INTEGRATION.md for the binding stubs.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller, 16-byte aligned at its base, valid until
+ *     `stream` reaches the call; nothing here allocates per call, synchronises, throws or exits;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value: OC_OK or a negative oc_status; oc_status_string() names it;
+ *   - an oc_layout is an immutable handle (host struct + a small device-side descriptor on the CUDA device
+ *     that was current at creation); calls are re-entrant and share no mutable global state;
+ *   - arrays are struct-of-arrays with a leading N; dtypes/shapes per env are exactly the reference's
+ *     `State` fields (overcooked.py:44-56), so a State pytree maps onto oc_state field by field.
+ */
+#ifndef OC_B200_H
+#define OC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_B200_VERSION 100          /* 0.1.0 */
+#define OC_MAX_DIM 16                /* height, width <= 16 (reference registry max: 10 x 11) */
+#define OC_MAX_CELLS 256
+#define OC_MAX_SPECIAL 16            /* pots, goals, onion piles, plate piles: at most 16 each */
+#define OC_PAD 4                     /* agent_view_size - 1 (overcooked.py:88, common.py:153-154) */
+#define OC_OBS_CHANNELS 26           /* overcooked.py:86 */
+
+typedef enum {
+    OC_OK = 0,
+    OC_ERR_INVALID_ARG = -1,         /* NULL pointer, N < 0, bad enum */
+    OC_ERR_UNSUPPORTED_LAYOUT = -2,  /* see oc_layout_create */
+    OC_ERR_CUDA = -3,                /* a CUDA runtime call failed; cudaGetLastError has the detail */
+    OC_ERR_ALIGNMENT = -4,           /* a base pointer is not 16-byte aligned */
+    OC_ERR_NO_DEVICE = -5            /* no usable sm_100 device: there is NO CPU fallback */
+} oc_status;
+
+typedef enum {
+    OC_PRNG_THREEFRY_LEGACY = 0,         /* jax_threefry_partitionable=False (default for jax < 0.5.0) */
+    OC_PRNG_THREEFRY_PARTITIONABLE = 1   /* jax_threefry_partitionable=True  (default for jax >= 0.5.0) */
+} oc_prng_mode;
+
+/* Host-side description of an environment: the eight layout fields the reference env reads
+ * (layouts.py:4-58, 79-127) plus the constructor arguments of `Overcooked` (overcooked.py:71-78).
+ * Index arrays are HOST pointers to flat cell indices (row * width + col), copied at creation. */
+typedef struct {
+    int32_t height, width;
+    int32_t n_wall, n_goal, n_pot, n_onion_pile, n_plate_pile;
+    const int32_t *wall_idx;
+    const int32_t *agent_idx;        /* exactly 2 */
+    const int32_t *goal_idx;
+    const int32_t *pot_idx;
+    const int32_t *onion_pile_idx;
+    const int32_t *plate_pile_idx;
+    int32_t random_reset;            /* overcooked.py:75  */
+    int32_t max_steps;               /* overcooked.py:76  */
+    int32_t task_id;                 /* overcooked.py:77  */
+    int32_t prng_mode;               /* oc_prng_mode */
+} oc_layout_desc;
+
+typedef struct oc_layout oc_layout;  /* opaque */
+
+/* Batched `State` (overcooked.py:44-56), leading N on every array. */
+typedef struct {
+    uint32_t *agent_pos;     /* [N,2,2] (x, y) per agent        */
+    int8_t   *agent_dir;     /* [N,2,2] DIR_TO_VEC[agent_dir_idx] */
+    int32_t  *agent_dir_idx; /* [N,2]   */
+    int32_t  *agent_inv;     /* [N,2]   */
+    uint32_t *goal_pos;      /* [N,G,2] static per layout       */
+    uint32_t *pot_pos;       /* [N,P,2] static per layout       */
+    uint8_t  *wall_map;      /* [N,h,w] bool, static per layout */
+    uint8_t  *maze_map;      /* [N,h+8,w+8,3]                   */
+    int32_t  *time;          /* [N]     */
+    uint8_t  *terminal;      /* [N] bool */
+    int32_t  *task_id;       /* [N]     */
+} oc_state;
+
+/* Optional extras of oc_step: the LogWrapper bookkeeping (wrappers/baselines.py:75-107) fused into the
+ * step, and exact integer rollout statistics for the multi-GPU reduction.  Any pointer may be NULL. */
+typedef struct {
+    float   *episode_returns;           /* [N,2] in/out */
+    float   *episode_lengths;           /* [N,2] in/out */
+    float   *returned_episode_returns;  /* [N,2] in/out */
+    float   *returned_episode_lengths;  /* [N,2] in/out */
+    uint8_t *returned_episode;          /* [N,2] out (bool) */
+    /* int64[8] accumulators, atomically added to: [0] finished episodes, [1] sum of sparse reward,
+     * [2] sum shaped agent_0, [3] sum shaped agent_1, [4] sum returned_episode_returns[:,0] over finished
+     * episodes, [5] sum returned_episode_lengths[:,0] over finished episodes, [6] env-steps, [7] reserved.
+     * All addends are integers, so the totals are order-independent and bit-reproducible. */
+    long long *stats;
+} oc_step_extras;
+
+typedef struct {
+    int32_t height, width, n_goal, n_pot;
+    int64_t map_bytes_per_env;       /* (h+8)*(w+8)*3 */
+    int64_t obs_bytes_per_agent;     /* h*w*26        */
+    int64_t algorithmic_bytes;       /* 58*h*w + 117 per env-step */
+    int32_t envs_per_warp, warps_per_cta, smem_bytes_per_cta;
+} oc_layout_info;
+
+/* Build a layout handle on the current CUDA device.
+ * OC_ERR_UNSUPPORTED_LAYOUT unless: 1 <= h,w <= OC_MAX_DIM; exactly two agent cells, distinct, not walls;
+ * 1 <= n_pot <= OC_MAX_SPECIAL (the reference itself needs >= 1 pot, common.py:128-131), other lists
+ * <= OC_MAX_SPECIAL; every goal / pile / pot cell is listed in wall_idx (layouts.py:116-118 guarantees it for
+ * grid layouts); every border cell of the grid is a wall, so an agent never faces outside the grid
+ * (true for all 38 registered layouts and for anything produced by pad_observation_space); max_steps >= 1. */
+int  oc_layout_create(const oc_layout_desc *desc, oc_layout **out);
+void oc_layout_destroy(oc_layout *layout);
+int  oc_layout_query(const oc_layout *layout, oc_layout_info *info);
+
+/* env.reset under vmap: overcooked.py:136-248.  keys u32[N,2].  Writes every field of `out` (the whole
+ * padded maze_map included) and both observations u8[N,h,w,26]. */
+int oc_reset(const oc_layout *layout, int64_t N, const uint32_t *keys, oc_state out,
+             uint8_t *obs0, uint8_t *obs1, void *stream);
+
+/* env.step under vmap: multi_agent_env.py:41-69 -> overcooked.py:106-134 (step_env), :366-514 (step_agents),
+ * :516-642 (process_interact), :250-364 (get_obs), with auto-reset from `split(key)[1]`.
+ *   act0/act1     i32[N], values 0..5 (overcooked.py:93-100)
+ *   reset_state   NULL, or the caller-supplied `reset_state` of multi_agent_env.py:47,55-59
+ *   out           may alias `in` field by field (the fast path: XLA input_output_aliases / donated scan
+ *                 carries).  Where a field of `out` differs from `in`, it is first copied device-to-device.
+ *   reward f32[N] (same value for both agents, overcooked.py:124), shaped0/shaped1 f32[N]
+ *   (info["shaped_reward"]), done u8[N] (dones["__all__"] == dones[agent_i]).
+ * State invariants of SURVEY.md App. A.8 are assumed on input (every state produced by oc_reset / oc_step
+ * satisfies them); the static fields goal_pos / pot_pos / wall_map are taken from the layout. */
+int oc_step(const oc_layout *layout, int64_t N, const uint32_t *keys, oc_state in,
+            const int32_t *act0, const int32_t *act1, const oc_state *reset_state, oc_state out,
+            uint8_t *obs0, uint8_t *obs1, float *reward, float *shaped0, float *shaped1, uint8_t *done,
+            const oc_step_extras *extras, void *stream);
+
+/* env.get_obs under vmap: overcooked.py:250-364. */
+int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream);
+
+/* jax.random.split(key, num)[first : first+count] on the device (callers: IPPO_CL.py:477,535;
+ * wrappers/baselines.py:202,207).  `key` is a DEVICE pointer to u32[2]; out u32[count,2] must not alias it.
+ * Row i depends only on (key, i, num), so a GPU holding envs [first, first+count) of a global batch of
+ * `num` derives exactly the keys the single-device program would. */
+int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first, int64_t count,
+                  uint32_t *out, void *stream);
+
+const char *oc_status_string(int status);
+int oc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OC_B200_H */

@@ -1,0 +1,942 @@
+// oc_b200.cu -- hand-written sm_100a kernels + the C ABI (include/oc_b200.h) for the batched Overcooked step.
+//
+// What the kernels restate (reference file:line, relative to jax_marl/environments/):
+//   step        multi_agent_env.py:41-69 (key split, auto-reset select) -> overcooked_environment/overcooked.py
+//               :106-134 step_env, :366-514 step_agents, :516-642 process_interact, :488-500 pot timers
+//   reset       overcooked.py:136-248 + common.py:76-170 make_overcooked_map
+//   get_obs     overcooked.py:250-364 (26-channel per-agent observation)
+//   LogWrapper  ../wrappers/baselines.py:75-107 (optional epilogue)
+//   PRNG        jax.random.split / randint / choice on threefry2x32 (jax is not vendored in the reference;
+//               restated from the published algorithm, both `jax_threefry_partitionable` settings)
+//
+// Design (DESIGN.md has the long form):
+//   * one WARP owns a tile of `epw` consecutive environments; lanes 2e / 2e+1 are agent_0 / agent_1 of env e.
+//     Movement, collision/swap and the Alice-before-Bob interact ordering are resolved with __shfl_xor_sync
+//     between the two lanes of a pair; whole-warp votes skip the reset and conflict paths.
+//   * the only part of maze_map that can ever change is the h x w interior; the warp stages the byte span that
+//     covers the interior rows (word-granular, coalesced) in shared memory, updates it there, emits the
+//     observations from it and writes the span back in place.  The constant 4-cell wall ring is never touched.
+//   * observations are the HBM roofline term.  Each cell's 26 channel bytes are a pure function of a small
+//     "cell code" (object / pot status / agent x direction x inventory), so a 68-entry record table in shared
+//     memory turns the observation into table copies: one lane assembles a PAIR of cells (52 B = 13 words,
+//     conflict-free in shared memory), both agents' views are staged per tile and leave the SM as two bulk
+//     asynchronous copies (cp.async.bulk.global.shared::cta -- the TMA engine; SASS UBLKCP), i.e. full-line
+//     coalesced writes with no per-thread store instructions.
+//   * auto-reset is fused: envs whose episode ended rebuild their interior from a per-layout template and draw
+//     direction / position / pot status / inventory with an in-kernel threefry2x32.
+#include "oc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int kNumCodes = 68;        // 0..10 objects, 11..34 pot status 0..23, 35..66 agent(which,dir,inv), 67 spare
+constexpr int kRecWords = 16;        // [0..7] record at byte offset 0, [8..15] same record shifted by 2 bytes
+constexpr int kCodePot = 11;
+constexpr int kCodeAgent = 35;
+constexpr int kMaxSpanBytes = ((OC_MAX_DIM - 1) * (OC_MAX_DIM + 2 * OC_PAD) + OC_MAX_DIM) * 3;   // 1128
+constexpr int kMaxMapBytes = (OC_MAX_DIM + 2 * OC_PAD) * (OC_MAX_DIM + 2 * OC_PAD) * 3;          // 1728
+constexpr int kWarpsPerCta = 4;
+
+struct DevLayout {
+    int h, w, C, WP;
+    int map_bytes, span_off, span_len, span_words, span_stride;
+    int n_pot, n_goal;
+    int max_steps, random_reset, task_id, prng_mode;
+    int agent_cell[2];
+    unsigned magic_C, magic_w, magic_sw;      // ceil(2^32 / d) for d = C, w, span_words
+    unsigned wall_bits[8], blocked_bits[8];   // wall_map; wall_map | goal cells (movement blocking)
+    unsigned short pot_cell[OC_MAX_SPECIAL];
+    unsigned short goal_cell[OC_MAX_SPECIAL];
+    unsigned rec[kNumCodes][kRecWords];
+    unsigned char tmpl_span[kMaxSpanBytes + 8];   // interior span right after a reset, without agents, pots = 23
+    unsigned char tmpl_full[kMaxMapBytes];        // whole padded map, same contents (oc_reset initialisation)
+};
+
+struct KParams {
+    const DevLayout *L;
+    long long N;
+    long long n_tiles;
+    const uint32_t *keys;
+    oc_state st;
+    oc_state rs;
+    int has_rs;
+    const int32_t *act0, *act1;
+    uint8_t *obs0, *obs1;
+    float *reward, *shaped0, *shaped1;
+    uint8_t *done;
+    oc_step_extras ex;
+    int epw;        // environments per warp tile: 16, 8, 4 or 2
+    int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
+    int warp_bytes; // shared memory per warp
+    // scalar copies of the layout, so the hot loop reads them from the constant bank
+    int h, w, C, WP, map_bytes, span_off, span_len, span_words, span_stride, n_pot, max_steps, random_reset, part;
+    int agent_cell0, agent_cell1;
+    unsigned magic_C, magic_w, magic_sw;
+};
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBS = 2 };
+
+// ------------------------------------------------------------------------------------------------ PRNG
+
+__device__ __forceinline__ void tf2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t &y0, uint32_t &y1) {
+    const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+#define OC_MIX(r) x0 += x1; x1 = __funnelshift_l(x1, x1, r); x1 ^= x0;
+    x0 += k0; x1 += k1;
+    OC_MIX(13) OC_MIX(15) OC_MIX(26) OC_MIX(6)
+    x0 += k1; x1 += k2 + 1u;
+    OC_MIX(17) OC_MIX(29) OC_MIX(16) OC_MIX(24)
+    x0 += k2; x1 += k0 + 2u;
+    OC_MIX(13) OC_MIX(15) OC_MIX(26) OC_MIX(6)
+    x0 += k0; x1 += k1 + 3u;
+    OC_MIX(17) OC_MIX(29) OC_MIX(16) OC_MIX(24)
+    x0 += k1; x1 += k2 + 4u;
+    OC_MIX(13) OC_MIX(15) OC_MIX(26) OC_MIX(6)
+    x0 += k2; x1 += k0 + 5u;
+#undef OC_MIX
+    y0 = x0; y1 = x1;
+}
+
+// key, sub = jax.random.split(key)
+__device__ __forceinline__ void split2(int part, uint32_t &k0, uint32_t &k1, uint32_t &s0, uint32_t &s1) {
+    uint32_t a, b, c, d;
+    if (part) {
+        tf2x32(k0, k1, 0u, 0u, a, b);
+        tf2x32(k0, k1, 0u, 1u, c, d);
+        k0 = a; k1 = b; s0 = c; s1 = d;
+    } else {
+        tf2x32(k0, k1, 0u, 2u, a, b);
+        tf2x32(k0, k1, 1u, 3u, c, d);
+        k0 = a; k1 = c; s0 = b; s1 = d;
+    }
+}
+
+// word j of random_bits(key, n) (32-bit)
+__device__ __forceinline__ uint32_t bits_at(int part, uint32_t k0, uint32_t k1, int n, int j) {
+    uint32_t a, b;
+    if (part) { tf2x32(k0, k1, 0u, (uint32_t)j, a, b); return a ^ b; }
+    const int m = (n + 1) >> 1;
+    if (j < m) { tf2x32(k0, k1, (uint32_t)j, (j + m < n) ? (uint32_t)(j + m) : 0u, a, b); return a; }
+    tf2x32(k0, k1, (uint32_t)(j - m), (uint32_t)j, a, b);
+    return b;
+}
+
+// element j of jax.random.randint(key, (n,), 0, span)
+__device__ __forceinline__ int randint_at(int part, uint32_t k0, uint32_t k1, int n, int j, uint32_t span) {
+    uint32_t s0, s1;
+    split2(part, k0, k1, s0, s1);          // k = first row (higher bits), s = second row (lower bits)
+    uint32_t mult = 65536u % span;
+    mult = (mult * mult) % span;
+    const uint32_t lb = bits_at(part, s0, s1, n, j);
+    uint32_t off = lb % span;
+    if (mult != 0u) off += (bits_at(part, k0, k1, n, j) % span) * mult;
+    return (int)(off % span);
+}
+
+// ------------------------------------------------------------------------------------------ small helpers
+
+__device__ __forceinline__ unsigned fastdiv(unsigned x, unsigned magic) { return __umulhi(x, magic); }
+__device__ __forceinline__ int dir_x(int d) { return (d == 2) - (d == 3); }
+__device__ __forceinline__ int dir_y(int d) { return (d == 1) - (d == 0); }
+__device__ __forceinline__ int obj_colour(int o) { return (int)((0x06716644500ull >> (4 * o)) & 0xFull); }  // common.py:51-63
+__device__ __forceinline__ int inv_code(int inv) { return inv == 9 ? 3 : ((inv >> 1) & 3); }               // 1,3,5,9 -> 0..3
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct Interact { int obj, status, inv, delivery, shaped, write; };
+
+// overcooked.py:516-642 for one agent facing a cell holding (obj, status); `wall` = wall_map at that cell.
+__device__ __forceinline__ Interact interact_cell(int obj, int status, int inv, bool wall) {
+    const bool is_pot = obj == 8, is_goal = obj == 7, is_agent = obj == 10;
+    const bool is_pile = (obj == 6) | (obj == 4);
+    const bool pickable = (obj == 5) | (obj == 3) | (obj == 9);
+    const bool is_table = wall & !is_pot;
+    const bool table_empty = (obj == 2) | (obj == 1);
+    const bool case1 = is_pot & (status > 20) & (inv == 3);      // onion into a pot that is not full
+    const bool case2 = is_pot & (status == 0) & (inv == 5);      // plate a finished soup
+    const bool pickup = is_table & !table_empty & (inv == 1) & (is_pile | pickable);
+    const bool drop = is_table & table_empty & (inv != 1);
+    const bool delivery = is_table & is_goal & (inv == 9);
+    Interact r;
+    r.status = case1 ? status - 1 : (case2 ? 23 : status);
+    int ninv = case1 ? 1 : (case2 ? 9 : inv);
+    r.obj = obj;
+    if (pickup) { r.obj = is_pile ? obj : 2; ninv = (obj == 6) ? 5 : ((obj == 4) ? 3 : obj); }
+    if (drop) { r.obj = inv; ninv = 1; }
+    if (delivery) ninv = 1;
+    r.inv = ninv;
+    r.delivery = delivery;
+    // :568-569; the plate-pickup bonus (:616-628) is identically zero: the ring's colour byte is 5
+    r.shaped = case1 ? 3 : (case2 ? 5 : 0);
+    r.write = !is_agent;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+
+template <int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const DevLayout *__restrict__ L = p.L;
+    uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *s_bits = s_rec + kNumCodes * kRecWords;                    // [0..7] wall, [8..15] blocked
+    unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
+    constexpr int kHdrBytes = kNumCodes * kRecWords * 4 + 64 + 32;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {   // CTA-wide constants -> shared memory
+        const uint4 *src = reinterpret_cast<const uint4 *>(&L->rec[0][0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_rec);
+        for (int i = tid; i < kNumCodes * kRecWords / 4; i += kWarpsPerCta * 32) dst[i] = __ldg(src + i);
+        if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
+        if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
+    }
+    const int h = p.h, w = p.w, C = p.C, WP = p.WP;
+    const int epw = p.epw;
+    const int span_stride = p.span_stride, span_words = p.span_words;
+    const int part = p.part;
+    const int view_bytes = epw * C * OC_OBS_CHANNELS;
+    unsigned char *wbase = smem + kHdrBytes + (size_t)warp * p.warp_bytes;
+    uint32_t *stage0 = reinterpret_cast<uint32_t *>(wbase);
+    uint32_t *stage1 = reinterpret_cast<uint32_t *>(wbase + view_bytes);
+    unsigned char *smap = wbase + 2 * view_bytes;
+    uint32_t *smap_w = reinterpret_cast<uint32_t *>(smap);
+    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap + epw * span_stride);   // [2*epw] packed agent state
+    __syncthreads();
+
+    const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
+    bool bulk_pending = false;
+
+    for (long long tile = (long long)blockIdx.x * kWarpsPerCta + warp; tile < p.n_tiles;
+         tile += (long long)gridDim.x * kWarpsPerCta) {
+        const long long env0 = tile * epw;
+        const int n_valid = (int)min((long long)epw, p.N - env0);
+        const bool active = e < n_valid;
+        const int es = active ? e : 0;            // idle lanes shadow env 0 of the tile (reads only)
+        const long long env = env0 + es;
+        // byte offset (within maze_map) of this env's interior span, and its word misalignment
+        const long long gb_lane = env * (long long)p.map_bytes + p.span_off;
+        const int shift_lane = (int)(gb_lane & 3);
+        unsigned char *my_span = smap + es * span_stride + shift_lane;
+
+        // ---------------------------------------------------------------- (1) stage the interior spans
+        if (MODE != MODE_RESET) {
+            const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map);
+            const int total = n_valid * span_words;
+            for (int f = lane; f < total; f += 32) {
+                const int el = (int)fastdiv((unsigned)f, p.magic_sw);
+                const int k = f - el * span_words;
+                const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
+                smap_w[el * (span_stride >> 2) + k] = mw[(gb >> 2) + k];   // plain load: rewritten in place below
+            }
+        }
+
+        // ---------------------------------------------------------------- (2) per-agent state
+        int px = 0, py = 0, dx = 0, dy = 0, di = 0, inv = 1, act = 4, t = 0;
+        if (active && MODE != MODE_RESET) {
+            const uint2 pp = reinterpret_cast<const uint2 *>(p.st.agent_pos)[env * 2 + ai];
+            px = (int)pp.x; py = (int)pp.y;
+            di = p.st.agent_dir_idx[env * 2 + ai];
+            inv = p.st.agent_inv[env * 2 + ai];
+            t = p.st.time[env];
+            if (MODE == MODE_STEP) {
+                const char2 dd = reinterpret_cast<const char2 *>(p.st.agent_dir)[env * 2 + ai];
+                dx = dd.x; dy = dd.y;
+                act = __ldg((ai ? p.act1 : p.act0) + env);
+                act = clampi(act, 0, 5);
+            }
+        }
+        __syncwarp();
+
+        int nx = px, ny = py, ndi = di, ninv = inv, t_out = t, term_out = 0;
+        bool done = (MODE == MODE_RESET);
+        int rew = 0, shaped = 0;
+
+        if (MODE == MODE_STEP) {
+            // ------------------------------------------------------------ movement (overcooked.py:370-431)
+            const bool is_move = act < 4;
+            const int cx = clampi(px + (is_move ? dir_x(act) : dx), 0, w - 1);
+            const int cy = clampi(py + (is_move ? dir_y(act) : dy), 0, h - 1);
+            const int cc = cy * w + cx;
+            const bool blocked = (s_bits[8 + (cc >> 5)] >> (cc & 31)) & 1u;
+            const bool bounced = blocked | !is_move;
+            const int tx = bounced ? px : cx, ty = bounced ? py : cy;
+            const int otx = __shfl_xor_sync(0xffffffffu, tx, 1), oty = __shfl_xor_sync(0xffffffffu, ty, 1);
+            const int opx = __shfl_xor_sync(0xffffffffu, px, 1), opy = __shfl_xor_sync(0xffffffffu, py, 1);
+            const bool collision = (tx == otx) & (ty == oty);
+            const bool swapped = (tx == opx) & (ty == opy) & (otx == px) & (oty == py);
+            const bool stay = collision | swapped;
+            nx = stay ? px : tx; ny = stay ? py : ty;
+            ndi = is_move ? act : di;                                       // :434 turn even when bounced
+
+            // ------------------------------------------------------------ interact (:437-468, :516-642)
+            const int fx = clampi(px + dx, 0, w - 1), fy = clampi(py + dy, 0, h - 1);   // old pos + old dir
+            const int fc = fy * w + fx;
+            unsigned char *cp = my_span + (fy * WP + fx) * 3;
+            const bool wallbit = (s_bits[fc >> 5] >> (fc & 31)) & 1u;
+            const bool do_int = active & (act == 5);
+            Interact r = interact_cell(cp[0], cp[2], inv, wallbit);
+            if (do_int && ai == 0 && r.write) { cp[0] = (unsigned char)r.obj; cp[1] = (unsigned char)obj_colour(r.obj); cp[2] = (unsigned char)r.status; }
+            __syncwarp();
+            const int a_fc = __shfl_sync(0xffffffffu, fc, lane & ~1);
+            const int a_did = __shfl_sync(0xffffffffu, (int)do_int, lane & ~1);
+            if (do_int && ai == 1) {
+                if (a_did && a_fc == fc) r = interact_cell(cp[0], cp[2], inv, wallbit);   // Bob sees Alice's update
+                if (r.write) { cp[0] = (unsigned char)r.obj; cp[1] = (unsigned char)obj_colour(r.obj); cp[2] = (unsigned char)r.status; }
+            }
+            __syncwarp();
+            if (do_int) { ninv = r.inv; rew = r.delivery ? 20 : 0; shaped = r.shaped; }
+
+            // ------------------------------------------------------------ redraw agents (:470-486)
+            if (active) { unsigned char *c0 = my_span + (py * WP + px) * 3; c0[0] = 1; c0[1] = 0; c0[2] = 0; }
+            __syncwarp();
+            if (active) { unsigned char *c1 = my_span + (ny * WP + nx) * 3; c1[0] = 10; c1[1] = (unsigned char)(2 * ai); c1[2] = (unsigned char)ndi; }
+            __syncwarp();
+            // ------------------------------------------------------------ pot timers (:488-500)
+            if (active) {
+                for (int q = ai; q < p.n_pot; q += 2) {
+                    const int pc = s_pot[q];
+                    const int pyy = (int)fastdiv((unsigned)pc, p.magic_w), pxx = pc - pyy * w;
+                    unsigned char *c = my_span + (pyy * WP + pxx) * 3;
+                    const int s = c[2];
+                    if (s >= 1 && s <= 20) c[2] = (unsigned char)(s - 1);
+                }
+            }
+            rew += __shfl_xor_sync(0xffffffffu, rew, 1);                   // :502 reward = alice + bob
+            t_out = t + 1;                                                  // :118
+            done = t_out >= p.max_steps;                                    // :120, :644-647
+            __syncwarp();
+        }
+
+        // -------------------------------------------------------------------- (3) reset (overcooked.py:136-248)
+        if (MODE != MODE_OBS) {
+            const unsigned done_mask = __ballot_sync(0xffffffffu, done && active);
+            if (done_mask) {
+                if (MODE == MODE_STEP && p.has_rs) {
+                    // multi_agent_env.py:55-59: caller-supplied reset_state replaces reset(key_reset)
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.rs.maze_map);
+                    for (int el = 0; el < n_valid; ++el) {
+                        if (!((done_mask >> (2 * el)) & 1u)) continue;
+                        const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
+                        for (int k = lane; k < span_words; k += 32) smap_w[el * (span_stride >> 2) + k] = __ldg(rw + (gb >> 2) + k);
+                    }
+                    if (done && active) {
+                        const uint2 pp = __ldg(reinterpret_cast<const uint2 *>(p.rs.agent_pos) + env * 2 + ai);
+                        nx = (int)pp.x; ny = (int)pp.y;
+                        ndi = __ldg(p.rs.agent_dir_idx + env * 2 + ai);
+                        ninv = __ldg(p.rs.agent_inv + env * 2 + ai);
+                        t_out = __ldg(p.rs.time + env);
+                        term_out = __ldg(p.rs.terminal + env);
+                    }
+                    __syncwarp();
+                } else {
+                    // template interior for every finished env (warp-cooperative byte copy)
+                    for (int el = 0; el < n_valid; ++el) {
+                        if (!((done_mask >> (2 * el)) & 1u)) continue;
+                        const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
+                        unsigned char *dst = smap + el * span_stride + (int)(gb & 3);
+                        for (int k = lane; k < p.span_len; k += 32) dst[k] = __ldg(L->tmpl_span + k);
+                    }
+                    __syncwarp();
+                    if (done && active) {
+                        uint32_t k0 = __ldg(p.keys + env * 2), k1 = __ldg(p.keys + env * 2 + 1);
+                        uint32_t s0, s1;
+                        if (MODE == MODE_STEP) { split2(part, k0, k1, s0, s1); k0 = s0; k1 = s1; }   // key_reset
+                        uint32_t a0, a1, d0, d1, q0, q1, i0, i1;
+                        split2(part, k0, k1, a0, a1);      // :164 agent cells
+                        split2(part, k0, k1, d0, d1);      // :173 directions
+                        split2(part, k0, k1, q0, q1);      // :197 pot status
+                        split2(part, k0, k1, i0, i1);      // :225 inventories
+                        ndi = randint_at(part, d0, d1, 2, ai, 4u);                      // :174
+                        int cell = ai ? p.agent_cell1 : p.agent_cell0;
+                        ninv = 1;
+                        if (p.random_reset) {
+                            // :165-169 choice(p = free cells, replace=False): the two largest 23-bit mantissas,
+                            // ties to the lower cell index
+                            unsigned long long b1 = 0ull, b2 = 0ull;
+                            const int m = (C + 1) >> 1;
+                            const int nblk = part ? C : m;
+                            for (int j = ai; j < nblk; j += 2) {
+                                uint32_t y0, y1;
+                                int c0, c1;
+                                if (part) { tf2x32(a0, a1, 0u, (uint32_t)j, y0, y1); y0 ^= y1; c0 = j; c1 = -1; }
+                                else { tf2x32(a0, a1, (uint32_t)j, (j + m < C) ? (uint32_t)(j + m) : 0u, y0, y1); c0 = j; c1 = (j + m < C) ? j + m : -1; }
+                                #pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int c = u ? c1 : c0;
+                                    const uint32_t bits = u ? y1 : y0;
+                                    if (c < 0) continue;
+                                    if ((s_bits[c >> 5] >> (c & 31)) & 1u) continue;   // walls have p = 0
+                                    const unsigned long long key = ((unsigned long long)((bits >> 9) + 1u) << 32) | (uint32_t)(~(uint32_t)c);
+                                    if (key > b1) { b2 = b1; b1 = key; } else if (key > b2) { b2 = key; }
+                                }
+                            }
+                            const unsigned long long o1 = __shfl_xor_sync(done_mask, b1, 1);
+                            const unsigned long long o2 = __shfl_xor_sync(done_mask, b2, 1);
+                            const unsigned long long first = b1 > o1 ? b1 : o1;
+                            const unsigned long long second = b1 > o1 ? (b2 > o1 ? b2 : o1) : (o2 > b1 ? o2 : b1);
+                            cell = (int)(~(uint32_t)((ai ? second : first) & 0xffffffffull));
+                            const int it = randint_at(part, i0, i1, 2, ai, 4u);         // :226-230: [1,3,5,9][it]
+                            ninv = it == 3 ? 9 : 2 * it + 1;
+                            for (int q = ai; q < p.n_pot; q += 2) {                     // :200
+                                const int pc = s_pot[q];
+                                const int pyy = (int)fastdiv((unsigned)pc, p.magic_w), pxx = pc - pyy * w;
+                                my_span[(pyy * WP + pxx) * 3 + 2] = (unsigned char)randint_at(part, q0, q1, p.n_pot, q, 24u);
+                            }
+                        }
+                        ny = (int)fastdiv((unsigned)cell, p.magic_w); nx = cell - ny * w;    // :170
+                        unsigned char *c1 = my_span + (ny * WP + nx) * 3;                    // common.py:99-105
+                        c1[0] = 10; c1[1] = (unsigned char)(2 * ai); c1[2] = (unsigned char)ndi;
+                        t_out = 0;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
+        {
+            const int urg = (p.max_steps - t_out) < 40;                                       // :311
+            if (active)
+                s_ap[lane] = (uint32_t)nx | ((uint32_t)ny << 4) | ((uint32_t)ndi << 8) | ((uint32_t)inv_code(ninv) << 10) |
+                             ((uint32_t)urg << 12);
+            if (bulk_pending) {   // the previous tile's bulk copies must have finished READING the staging buffers
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bulk_pending = false;
+            }
+            __syncwarp();
+            const int n_cells = n_valid * C;
+            const int n_pairs = (n_cells + 1) >> 1;
+            for (int q = lane; q < n_pairs; q += 32) {
+                uint32_t rA0[8], rB0[8], rA1[8], rB1[8];
+                #pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int g = 2 * q + u;
+                    int code0 = 0, code1 = 0;
+                    uint32_t urgbit = 0;
+                    if (g < n_cells) {
+                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
+                        const int cell = g - el * C;
+                        const int y = (int)fastdiv((unsigned)cell, p.magic_w), x = cell - y * w;
+                        const uint32_t ap0 = s_ap[2 * el], ap1 = s_ap[2 * el + 1];
+                        const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
+                        const unsigned char *c = smap + el * span_stride + (int)(gb & 3) + (y * WP + x) * 3;
+                        const uint32_t xy = (uint32_t)x | ((uint32_t)y << 4);
+                        urgbit = (ap0 >> 12) & 1u;
+                        if ((ap0 & 0xffu) == xy) {            // :313-319 agent cells show the inventory
+                            code0 = kCodeAgent + (int)((ap0 >> 8) & 15u);
+                            code1 = code0 + 16;
+                        } else if ((ap1 & 0xffu) == xy) {
+                            code1 = kCodeAgent + (int)((ap1 >> 8) & 15u);
+                            code0 = code1 + 16;
+                        } else {
+                            const int o = c[0];
+                            code0 = (o == 8) ? kCodePot + min((int)c[2], 23) : min(o, 10);
+                            code1 = code0;
+                        }
+                    }
+                    const uint4 *r0 = reinterpret_cast<const uint4 *>(s_rec + code0 * kRecWords + 8 * u);
+                    const uint4 *r1 = reinterpret_cast<const uint4 *>(s_rec + code1 * kRecWords + 8 * u);
+                    uint4 v0 = r0[0], v1 = r0[1], w0 = r1[0], w1 = r1[1];
+                    const uint32_t ub = urgbit << (u ? 24 : 8);                 // channel 25 (:311, :341)
+                    v1.z |= ub; w1.z |= ub;
+                    uint32_t *d0 = u ? rB0 : rA0, *d1 = u ? rB1 : rA1;
+                    d0[0] = v0.x; d0[1] = v0.y; d0[2] = v0.z; d0[3] = v0.w; d0[4] = v1.x; d0[5] = v1.y; d0[6] = v1.z; d0[7] = v1.w;
+                    d1[0] = w0.x; d1[1] = w0.y; d1[2] = w0.z; d1[3] = w0.w; d1[4] = w1.x; d1[5] = w1.y; d1[6] = w1.z; d1[7] = w1.w;
+                }
+                uint32_t *o0 = stage0 + q * 13, *o1 = stage1 + q * 13;
+                #pragma unroll
+                for (int k = 0; k < 6; ++k) { o0[k] = rA0[k]; o1[k] = rA1[k]; }
+                o0[6] = rA0[6] | rB0[0]; o1[6] = rA1[6] | rB1[0];
+                #pragma unroll
+                for (int k = 1; k < 7; ++k) { o0[6 + k] = rB0[k]; o1[6 + k] = rB1[k]; }
+            }
+            const size_t obs_off = (size_t)env0 * C * OC_OBS_CHANNELS;
+            if (p.bulk_ok && n_valid == epw) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage0)), "r"(view_bytes) : "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage1)), "r"(view_bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                bulk_pending = true;
+            } else {
+                // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular
+                __syncwarp();
+                const int nb = n_cells * OC_OBS_CHANNELS;   // even
+                const unsigned short *h0 = reinterpret_cast<const unsigned short *>(stage0);
+                const unsigned short *h1 = reinterpret_cast<const unsigned short *>(stage1);
+                unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + obs_off);
+                unsigned short *g1 = reinterpret_cast<unsigned short *>(p.obs1 + obs_off);
+                for (int k = lane; k < (nb >> 1); k += 32) { g0[k] = h0[k]; g1[k] = h1[k]; }
+            }
+        }
+
+        // ---------------------------------------------------------------- (5) write the state back, in place
+        if (MODE != MODE_OBS) {
+            __syncwarp();
+            uint32_t *mw = reinterpret_cast<uint32_t *>(p.st.maze_map);
+            const int total = n_valid * span_words;
+            for (int f = lane; f < total; f += 32) {
+                const int el = (int)fastdiv((unsigned)f, p.magic_sw);
+                const int k = f - el * span_words;
+                const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
+                mw[(gb >> 2) + k] = smap_w[el * (span_stride >> 2) + k];
+            }
+            if (active) {
+                reinterpret_cast<uint2 *>(p.st.agent_pos)[env * 2 + ai] = make_uint2((uint32_t)nx, (uint32_t)ny);
+                reinterpret_cast<char2 *>(p.st.agent_dir)[env * 2 + ai] = make_char2((signed char)dir_x(ndi), (signed char)dir_y(ndi));
+                p.st.agent_dir_idx[env * 2 + ai] = ndi;
+                p.st.agent_inv[env * 2 + ai] = ninv;
+                if (ai == 0) {
+                    p.st.time[env] = t_out;
+                    p.st.terminal[env] = (uint8_t)term_out;   // stepped: done is False; reset: False (overcooked.py:242)
+                }
+            }
+            if (MODE == MODE_STEP) {
+                int st_rr = 0, st_rl = 0;
+                if (active) {
+                    if (ai == 0) { p.reward[env] = (float)rew; p.done[env] = (uint8_t)done; }
+                    (ai ? p.shaped1 : p.shaped0)[env] = (float)shaped;
+                    if (p.ex.episode_returns) {   // wrappers/baselines.py:90-106, this lane = agent ai
+                        const long long j = env * 2 + ai;
+                        const float keep = done ? 0.f : 1.f, dn = done ? 1.f : 0.f;
+                        const float nr = p.ex.episode_returns[j] + (float)rew;
+                        const float nl = p.ex.episode_lengths[j] + 1.f;
+                        p.ex.episode_returns[j] = nr * keep;
+                        p.ex.episode_lengths[j] = nl * keep;
+                        const float rr = p.ex.returned_episode_returns[j] * keep + nr * dn;
+                        const float rl = p.ex.returned_episode_lengths[j] * keep + nl * dn;
+                        p.ex.returned_episode_returns[j] = rr;
+                        p.ex.returned_episode_lengths[j] = rl;
+                        if (p.ex.returned_episode) p.ex.returned_episode[j] = (uint8_t)done;
+                        if (ai == 0 && done) { st_rr = (int)rr; st_rl = (int)rl; }
+                    } else if (p.ex.returned_episode) {
+                        p.ex.returned_episode[env * 2 + ai] = (uint8_t)done;
+                    }
+                }
+                if (p.ex.stats) {   // exact integer partial sums, one atomic per warp and only when non-zero
+                    int v_done = (active && ai == 0 && done) ? 1 : 0;
+                    int v_rew = (active && ai == 0) ? rew : 0;
+                    int v_s0 = (active && ai == 0) ? shaped : 0;
+                    int v_s1 = (active && ai == 1) ? shaped : 0;
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        v_done += __shfl_xor_sync(0xffffffffu, v_done, o);
+                        v_rew += __shfl_xor_sync(0xffffffffu, v_rew, o);
+                        v_s0 += __shfl_xor_sync(0xffffffffu, v_s0, o);
+                        v_s1 += __shfl_xor_sync(0xffffffffu, v_s1, o);
+                        st_rr += __shfl_xor_sync(0xffffffffu, st_rr, o);
+                        st_rl += __shfl_xor_sync(0xffffffffu, st_rl, o);
+                    }
+                    if (lane == 0) {
+                        unsigned long long *s = reinterpret_cast<unsigned long long *>(p.ex.stats);
+                        if (v_done) atomicAdd(s + 0, (unsigned long long)v_done);
+                        if (v_rew) atomicAdd(s + 1, (unsigned long long)v_rew);
+                        if (v_s0) atomicAdd(s + 2, (unsigned long long)v_s0);
+                        if (v_s1) atomicAdd(s + 3, (unsigned long long)v_s1);
+                        if (st_rr) atomicAdd(s + 4, (unsigned long long)st_rr);
+                        if (st_rl) atomicAdd(s + 5, (unsigned long long)st_rl);
+                        atomicAdd(s + 6, (unsigned long long)n_valid);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// oc_reset pre-pass: constant ring + static State fields (the reset kernel then fills interior and dynamics)
+__global__ void oc_init_static_kernel(const DevLayout *__restrict__ L, long long N, oc_state st) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mb = L->map_bytes, C = L->C, w = L->w;
+    for (long long i = tid; i < N * mb; i += stride) st.maze_map[i] = L->tmpl_full[(int)(i % mb)];
+    for (long long i = tid; i < N * C; i += stride) {
+        const int c = (int)(i % C);
+        st.wall_map[i] = (uint8_t)((L->wall_bits[c >> 5] >> (c & 31)) & 1u);
+    }
+    for (long long i = tid; i < N * L->n_goal; i += stride) {
+        const int c = L->goal_cell[(int)(i % L->n_goal)];
+        st.goal_pos[2 * i] = (uint32_t)(c % w); st.goal_pos[2 * i + 1] = (uint32_t)(c / w);
+    }
+    for (long long i = tid; i < N * L->n_pot; i += stride) {
+        const int c = L->pot_cell[(int)(i % L->n_pot)];
+        st.pot_pos[2 * i] = (uint32_t)(c % w); st.pot_pos[2 * i + 1] = (uint32_t)(c / w);
+    }
+    for (long long i = tid; i < N; i += stride) st.task_id[i] = L->task_id;
+}
+
+// rows [first, first+count) of jax.random.split(key, num)
+__global__ void oc_split_kernel(int part, const uint32_t *__restrict__ key, long long num, long long first,
+                                long long count, uint32_t *__restrict__ out) {
+    const uint32_t k0 = __ldg(key), k1 = __ldg(key + 1);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += stride) {
+        const long long i = first + r;
+        uint32_t a, b;
+        if (part) {
+            tf2x32(k0, k1, 0u, (uint32_t)i, a, b);
+            out[2 * r] = a; out[2 * r + 1] = b;
+        } else {
+            #pragma unroll
+            for (int c = 0; c < 2; ++c) {   // flat word j of threefry_2x32(key, iota(2*num)): halves of `num` blocks
+                const long long j = 2 * i + c;
+                if (j < num) { tf2x32(k0, k1, (uint32_t)j, (uint32_t)(j + num), a, b); out[2 * r + c] = a; }
+                else { tf2x32(k0, k1, (uint32_t)(j - num), (uint32_t)j, a, b); out[2 * r + c] = b; }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ================================================================================================ host side
+
+struct oc_layout {
+    DevLayout host;
+    DevLayout *dev;
+    int device;
+    int epw;
+    int smem_bytes;
+    int warp_bytes;
+    int max_ctas;      // persistent-grid cap: SM count x resident CTAs per SM
+};
+
+namespace {
+
+constexpr int kHdrBytesHost = kNumCodes * kRecWords * 4 + 64 + 32;
+
+unsigned magic_of(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
+
+// one cell's 26 observation bytes for a given cell code, from agent_0's... "viewer's" perspective
+void fill_record(int code, unsigned char v[26]) {
+    std::memset(v, 0, 26);
+    auto env_obj = [&](int o) {   // overcooked.py:326-340 on o' (object id, or the inventory on an agent cell)
+        if (o == 8) v[10] = 1;
+        if (o == 2) v[11] = 1;
+        if (o == 4) v[12] = 1;
+        if (o == 6) v[14] = 1;
+        if (o == 7) v[15] = 1;
+        if (o == 5) v[22] = 1;
+        if (o == 3) v[23] = 1;
+    };
+    if (code < kCodePot) {
+        env_obj(code);
+        if (code == 9) { v[18] = 3; v[21] = 1; }          // dish on a counter: soup_loc (:302, :308, :310)
+    } else if (code < kCodeAgent) {
+        const int s = code - kCodePot;                      // pot with status s
+        v[10] = 1;
+        if (s >= 20) v[16] = (unsigned char)((23 - s) < 3 ? (23 - s) : 3);   // :306
+        else { v[18] = 3; v[20] = (unsigned char)s; v[21] = (s == 0); }       // :307-310
+    } else if (code < kCodeAgent + 32) {
+        const int k = code - kCodeAgent, which = k >> 4, dir = k & 3, ic = (k >> 2) & 3;
+        static const int items[4] = {1, 3, 5, 9};
+        v[which] = 1;                                       // :351 / :357
+        v[2 + 4 * which + dir] = 1;                         // :345-347, :353 / :358
+        env_obj(items[ic]);
+        if (items[ic] == 9) { v[18] = 3; v[21] = 1; }       // held dish (:320-323)
+    }
+}
+
+int fail_cuda() { return OC_ERR_CUDA; }
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool state_ok(const oc_state &s) {
+    return s.agent_pos && s.agent_dir && s.agent_dir_idx && s.agent_inv && s.goal_pos && s.pot_pos && s.wall_map &&
+           s.maze_map && s.time && s.terminal && s.task_id;
+}
+
+bool state_aligned(const oc_state &s) {
+    return aligned16(s.agent_pos) && aligned16(s.agent_dir) && aligned16(s.agent_dir_idx) && aligned16(s.agent_inv) &&
+           aligned16(s.maze_map) && aligned16(s.time);
+}
+
+template <int MODE>
+int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
+    static bool attr_set[16][3] = {};
+    const DevLayout &H = lay->host;
+    kp.L = lay->dev;
+    kp.epw = lay->epw;
+    kp.warp_bytes = lay->warp_bytes;
+    kp.h = H.h; kp.w = H.w; kp.C = H.C; kp.WP = H.WP; kp.map_bytes = H.map_bytes; kp.span_off = H.span_off;
+    kp.span_len = H.span_len; kp.span_words = H.span_words; kp.span_stride = H.span_stride; kp.n_pot = H.n_pot;
+    kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
+    kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
+    kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
+    kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
+    long long ctas = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > lay->max_ctas) ctas = lay->max_ctas;
+    if (ctas < 1) return OC_OK;
+    if (lay->device < 16 && !attr_set[lay->device][MODE]) {
+        if (cudaFuncSetAttribute(oc_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail_cuda();
+        attr_set[lay->device][MODE] = true;
+    } else if (lay->device >= 16) {
+        if (cudaFuncSetAttribute(oc_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail_cuda();
+    }
+    oc_env_kernel<MODE><<<(unsigned)ctas, kWarpsPerCta * 32, lay->smem_bytes, stream>>>(kp);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : fail_cuda();
+}
+
+}  // namespace
+
+extern "C" {
+
+int oc_version(void) { return OC_B200_VERSION; }
+
+const char *oc_status_string(int s) {
+    switch (s) {
+        case OC_OK: return "ok";
+        case OC_ERR_INVALID_ARG: return "invalid argument";
+        case OC_ERR_UNSUPPORTED_LAYOUT: return "unsupported layout";
+        case OC_ERR_CUDA: return "CUDA runtime error";
+        case OC_ERR_ALIGNMENT: return "base pointer not 16-byte aligned";
+        case OC_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
+    if (!d || !out) return OC_ERR_INVALID_ARG;
+    *out = nullptr;
+    const int h = d->height, w = d->width;
+    if (h < 1 || w < 1 || h > OC_MAX_DIM || w > OC_MAX_DIM) return OC_ERR_UNSUPPORTED_LAYOUT;
+    const int C = h * w;
+    if (d->n_pot < 1 || d->n_pot > OC_MAX_SPECIAL || d->n_goal < 0 || d->n_goal > OC_MAX_SPECIAL ||
+        d->n_onion_pile < 0 || d->n_onion_pile > OC_MAX_SPECIAL || d->n_plate_pile < 0 ||
+        d->n_plate_pile > OC_MAX_SPECIAL || d->n_wall < 0 || d->max_steps < 1)
+        return OC_ERR_UNSUPPORTED_LAYOUT;
+    if (!d->agent_idx || !d->pot_idx || (d->n_wall && !d->wall_idx) || (d->n_goal && !d->goal_idx) ||
+        (d->n_onion_pile && !d->onion_pile_idx) || (d->n_plate_pile && !d->plate_pile_idx))
+        return OC_ERR_INVALID_ARG;
+    if (d->prng_mode != OC_PRNG_THREEFRY_LEGACY && d->prng_mode != OC_PRNG_THREEFRY_PARTITIONABLE)
+        return OC_ERR_INVALID_ARG;
+
+    std::vector<unsigned char> wall(C, 0);
+    for (int i = 0; i < d->n_wall; ++i) {
+        const int c = d->wall_idx[i];
+        if (c < 0 || c >= C) return OC_ERR_UNSUPPORTED_LAYOUT;
+        wall[c] = 1;
+    }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            if ((y == 0 || y == h - 1 || x == 0 || x == w - 1) && !wall[y * w + x]) return OC_ERR_UNSUPPORTED_LAYOUT;
+    auto special_ok = [&](const int32_t *idx, int n) {
+        for (int i = 0; i < n; ++i)
+            if (idx[i] < 0 || idx[i] >= C || !wall[idx[i]]) return false;
+        return true;
+    };
+    if (!special_ok(d->goal_idx, d->n_goal) || !special_ok(d->pot_idx, d->n_pot) ||
+        !special_ok(d->onion_pile_idx, d->n_onion_pile) || !special_ok(d->plate_pile_idx, d->n_plate_pile))
+        return OC_ERR_UNSUPPORTED_LAYOUT;
+    for (int i = 0; i < 2; ++i)
+        if (d->agent_idx[i] < 0 || d->agent_idx[i] >= C || wall[d->agent_idx[i]]) return OC_ERR_UNSUPPORTED_LAYOUT;
+    if (d->agent_idx[0] == d->agent_idx[1]) return OC_ERR_UNSUPPORTED_LAYOUT;
+    int n_free = 0;
+    for (int c = 0; c < C; ++c) n_free += !wall[c];
+    if (n_free < 2) return OC_ERR_UNSUPPORTED_LAYOUT;
+
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return OC_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OC_ERR_NO_DEVICE;
+    if (prop.major < 10) return OC_ERR_NO_DEVICE;
+
+    oc_layout *lay = new (std::nothrow) oc_layout();
+    if (!lay) return OC_ERR_INVALID_ARG;
+    DevLayout &L = lay->host;
+    std::memset(&L, 0, sizeof(L));
+    L.h = h; L.w = w; L.C = C; L.WP = w + 2 * OC_PAD;
+    L.map_bytes = (h + 2 * OC_PAD) * L.WP * 3;
+    L.span_off = (OC_PAD * L.WP + OC_PAD) * 3;
+    L.span_len = ((h - 1) * L.WP + w) * 3;
+    L.span_words = (L.span_len + 3 + 3) / 4;
+    L.span_stride = L.span_words * 4;
+    L.n_pot = d->n_pot; L.n_goal = d->n_goal;
+    L.max_steps = d->max_steps; L.random_reset = d->random_reset ? 1 : 0; L.task_id = d->task_id;
+    L.prng_mode = d->prng_mode;
+    L.agent_cell[0] = d->agent_idx[0]; L.agent_cell[1] = d->agent_idx[1];
+    L.magic_C = magic_of((unsigned)C); L.magic_w = magic_of((unsigned)w); L.magic_sw = magic_of((unsigned)L.span_words);
+    for (int c = 0; c < C; ++c)
+        if (wall[c]) { L.wall_bits[c >> 5] |= 1u << (c & 31); L.blocked_bits[c >> 5] |= 1u << (c & 31); }
+    for (int i = 0; i < d->n_goal; ++i) {
+        L.goal_cell[i] = (unsigned short)d->goal_idx[i];
+        L.blocked_bits[d->goal_idx[i] >> 5] |= 1u << (d->goal_idx[i] & 31);   // overcooked.py:381-391
+    }
+    for (int i = 0; i < d->n_pot; ++i) L.pot_cell[i] = (unsigned short)d->pot_idx[i];
+
+    // observation record table
+    for (int code = 0; code < kNumCodes; ++code) {
+        unsigned char v[32];
+        std::memset(v, 0, sizeof(v));
+        fill_record(code, v);
+        unsigned char a[32], b[32];
+        std::memset(a, 0, 32); std::memset(b, 0, 32);
+        std::memcpy(a, v, 26);
+        std::memcpy(b + 2, v, 26);
+        std::memcpy(&L.rec[code][0], a, 32);
+        std::memcpy(&L.rec[code][8], b, 32);
+    }
+    // post-reset map template (common.py:76-170), agents left out; pots at POT_EMPTY_STATUS
+    {
+        const int HP = h + 2 * OC_PAD, WP = L.WP;
+        unsigned char *m = L.tmpl_full;
+        for (int i = 0; i < HP * WP; ++i) { m[3 * i] = 2; m[3 * i + 1] = 5; m[3 * i + 2] = 0; }
+        auto put = [&](int c, int o, int col, int st) {
+            unsigned char *q = m + ((OC_PAD + c / w) * WP + OC_PAD + c % w) * 3;
+            q[0] = (unsigned char)o; q[1] = (unsigned char)col; q[2] = (unsigned char)st;
+        };
+        for (int c = 0; c < C; ++c) if (!wall[c]) put(c, 1, 0, 0);
+        for (int i = 0; i < d->n_goal; ++i) put(d->goal_idx[i], 7, 1, 0);
+        for (int i = 0; i < d->n_onion_pile; ++i) put(d->onion_pile_idx[i], 4, 4, 0);
+        for (int i = 0; i < d->n_plate_pile; ++i) put(d->plate_pile_idx[i], 6, 6, 0);
+        for (int i = 0; i < d->n_pot; ++i) put(d->pot_idx[i], 8, 7, 23);
+        std::memcpy(L.tmpl_span, m + L.span_off, (size_t)L.span_len);
+    }
+
+    // tile shape: the largest envs-per-warp that still leaves >= 4 CTAs (16 warps) resident per SM, subject to the
+    // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
+    const int smem_cap = 227 * 1024;
+    auto warp_bytes_for = [&](int e) { return ((2 * e * C * OC_OBS_CHANNELS + e * L.span_stride + 2 * e * 4) + 15) & ~15; };
+    auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
+    int epw = 0;
+    for (int e = 16; e >= 2; e >>= 1)
+        if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap / 4) { epw = e; break; }
+    if (!epw)
+        for (int e = 2; e <= 16; e <<= 1)
+            if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap) { epw = e; break; }
+    if (const char *ev = std::getenv("OC_B200_EPW")) {
+        const int v = std::atoi(ev);
+        if ((v == 2 || v == 4 || v == 8 || v == 16) && size_ok(v) &&
+            kHdrBytesHost + kWarpsPerCta * warp_bytes_for(v) <= smem_cap) epw = v;
+    }
+    if (!epw) { delete lay; return OC_ERR_UNSUPPORTED_LAYOUT; }
+    lay->epw = epw;
+    lay->warp_bytes = warp_bytes_for(epw);
+    lay->smem_bytes = kHdrBytesHost + kWarpsPerCta * lay->warp_bytes;
+    int per_sm = smem_cap / (lay->smem_bytes + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    lay->max_ctas = prop.multiProcessorCount * per_sm * 8;   // a few waves; the kernel grid-strides beyond that
+    lay->device = device;
+    if (cudaMalloc(&lay->dev, sizeof(DevLayout)) != cudaSuccess) { delete lay; return fail_cuda(); }
+    if (cudaMemcpy(lay->dev, &L, sizeof(DevLayout), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(lay->dev); delete lay; return fail_cuda();
+    }
+    *out = lay;
+    return OC_OK;
+}
+
+void oc_layout_destroy(oc_layout *lay) {
+    if (!lay) return;
+    if (lay->dev) cudaFree(lay->dev);
+    delete lay;
+}
+
+int oc_layout_query(const oc_layout *lay, oc_layout_info *info) {
+    if (!lay || !info) return OC_ERR_INVALID_ARG;
+    const DevLayout &L = lay->host;
+    info->height = L.h; info->width = L.w; info->n_goal = L.n_goal; info->n_pot = L.n_pot;
+    info->map_bytes_per_env = L.map_bytes;
+    info->obs_bytes_per_agent = (int64_t)L.C * OC_OBS_CHANNELS;
+    info->algorithmic_bytes = 58ll * L.C + 117;
+    info->envs_per_warp = lay->epw; info->warps_per_cta = kWarpsPerCta; info->smem_bytes_per_cta = lay->smem_bytes;
+    return OC_OK;
+}
+
+int oc_reset(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state out, uint8_t *obs0, uint8_t *obs1,
+             void *stream_) {
+    if (!lay || N < 0 || !keys || !state_ok(out) || !obs0 || !obs1) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    if (!state_aligned(out) || !aligned16(keys)) return OC_ERR_ALIGNMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    long long blocks = (N * lay->host.map_bytes + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    oc_init_static_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lay->dev, N, out);
+    if (cudaGetLastError() != cudaSuccess) return fail_cuda();
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.N = N; kp.keys = keys; kp.st = out; kp.obs0 = obs0; kp.obs1 = obs1;
+    kp.bulk_ok = aligned16(obs0) && aligned16(obs1);
+    return launch_env<MODE_RESET>(lay, kp, stream);
+}
+
+int oc_get_obs(const oc_layout *lay, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream_) {
+    if (!lay || N < 0 || !state_ok(in) || !obs0 || !obs1) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    if (!state_aligned(in)) return OC_ERR_ALIGNMENT;
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.N = N; kp.st = in; kp.obs0 = obs0; kp.obs1 = obs1;
+    kp.bulk_ok = aligned16(obs0) && aligned16(obs1);
+    return launch_env<MODE_OBS>(lay, kp, static_cast<cudaStream_t>(stream_));
+}
+
+int oc_step(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state in, const int32_t *act0,
+            const int32_t *act1, const oc_state *reset_state, oc_state out, uint8_t *obs0, uint8_t *obs1,
+            float *reward, float *shaped0, float *shaped1, uint8_t *done, const oc_step_extras *extras,
+            void *stream_) {
+    if (!lay || N < 0 || !keys || !state_ok(in) || !state_ok(out) || !act0 || !act1 || !obs0 || !obs1 || !reward ||
+        !shaped0 || !shaped1 || !done)
+        return OC_ERR_INVALID_ARG;
+    if (reset_state && !state_ok(*reset_state)) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    if (!state_aligned(in) || !state_aligned(out) || !aligned16(keys) || !aligned16(act0) || !aligned16(act1) ||
+        (reset_state && !state_aligned(*reset_state)))
+        return OC_ERR_ALIGNMENT;
+    if (extras) {
+        const bool any = extras->episode_returns || extras->episode_lengths || extras->returned_episode_returns ||
+                         extras->returned_episode_lengths;
+        const bool all = extras->episode_returns && extras->episode_lengths && extras->returned_episode_returns &&
+                         extras->returned_episode_lengths;
+        if (any && !all) return OC_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const DevLayout &L = lay->host;
+    // functional call: copy whatever is not aliased, then step `out` in place
+#define OC_COPY(field, bytes_per_env)                                                                            \
+    if ((const void *)out.field != (const void *)in.field) {                                                     \
+        if (cudaMemcpyAsync(out.field, in.field, (size_t)N * (bytes_per_env), cudaMemcpyDeviceToDevice, stream)  \
+            != cudaSuccess) return fail_cuda();                                                                  \
+    }
+    OC_COPY(agent_pos, 16) OC_COPY(agent_dir, 4) OC_COPY(agent_dir_idx, 8) OC_COPY(agent_inv, 8)
+    OC_COPY(goal_pos, (size_t)8 * L.n_goal) OC_COPY(pot_pos, (size_t)8 * L.n_pot) OC_COPY(wall_map, (size_t)L.C)
+    OC_COPY(maze_map, (size_t)L.map_bytes) OC_COPY(time, 4) OC_COPY(terminal, 1) OC_COPY(task_id, 4)
+#undef OC_COPY
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.N = N; kp.keys = keys; kp.st = out; kp.act0 = act0; kp.act1 = act1; kp.obs0 = obs0; kp.obs1 = obs1;
+    kp.reward = reward; kp.shaped0 = shaped0; kp.shaped1 = shaped1; kp.done = done;
+    if (reset_state) { kp.rs = *reset_state; kp.has_rs = 1; }
+    if (extras) kp.ex = *extras;
+    kp.bulk_ok = aligned16(obs0) && aligned16(obs1);
+    return launch_env<MODE_STEP>(lay, kp, stream);
+}
+
+int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first, int64_t count, uint32_t *out,
+                  void *stream_) {
+    if (!key || !out || num < 1 || first < 0 || count < 0 || first + count > num || num > 0x7fffffffll)
+        return OC_ERR_INVALID_ARG;
+    if (prng_mode != OC_PRNG_THREEFRY_LEGACY && prng_mode != OC_PRNG_THREEFRY_PARTITIONABLE) return OC_ERR_INVALID_ARG;
+    if (count == 0) return OC_OK;
+    long long blocks = (count + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    oc_split_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(prng_mode, key, num, first, count, out);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : fail_cuda();
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+"""Host-side mirror of the reference's Overcooked environment interface, backed by the sm_100a kernels.
+
+Same names, argument meaning and outputs as the reference (jax_marl/environments/overcooked_environment/
+overcooked.py:69-104 constructor, :136 reset, :106 / multi_agent_env.py:41-69 step, :250 get_obs; State :44-56),
+with two differences that follow from leaving JAX:
+
+  * arrays are torch CUDA tensors (torch is only the allocator / stream provider here), and
+  * batching is native instead of `jax.vmap`: every method takes any leading batch shape -- `key[..., 2]`,
+    `actions[agent][...]`, State fields with the same leading dims -- and `()` is the reference's un-vmapped
+    call.  `jaxovercooked_b200.vmap(env.step)` is provided so call sites written as
+    `jax.vmap(env.step, in_axes=(0, 0, 0))(keys, state, actions)` (baselines/IPPO_CL.py:538) keep their shape.
+
+All compute goes through the C ABI in include/oc_b200.h; there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import dataclasses
+from enum import IntEnum
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib
+from .layouts import Layout, overcooked_layouts, LAYOUT_FIELDS
+
+PAD = 4
+N_CHANNELS = 26
+
+# reference constants (overcooked.py:23-31, 59-66; common.py:10-22)
+BASE_REW_SHAPING_PARAMS = {"PLACEMENT_IN_POT_REW": 3, "PLATE_PICKUP_REWARD": 3, "SOUP_PICKUP_REWARD": 5,
+                           "DROP_COUNTER_REWARD": 0, "DISH_DISP_DISTANCE_REW": 0, "POT_DISTANCE_REW": 0,
+                           "SOUP_DISTANCE_REW": 0}
+POT_EMPTY_STATUS, POT_FULL_STATUS, POT_READY_STATUS, MAX_ONIONS_IN_POT = 23, 20, 0, 3
+URGENCY_CUTOFF, DELIVERY_REWARD = 40, 20
+OBJECT_TO_INDEX = {"unseen": 0, "empty": 1, "wall": 2, "onion": 3, "onion_pile": 4, "plate": 5, "plate_pile": 6,
+                   "goal": 7, "pot": 8, "dish": 9, "agent": 10}
+
+
+class Actions(IntEnum):
+    up = 0
+    down = 1
+    right = 2
+    left = 3
+    stay = 4
+    interact = 5
+    done = 6
+
+
+@dataclasses.dataclass
+class State:
+    """overcooked.py:44-56.  Per-env dtypes/shapes: agent_pos u32[2,2] (x,y), agent_dir i8[2,2],
+    agent_dir_idx i32[2], agent_inv i32[2], goal_pos u32[G,2], pot_pos u32[P,2], wall_map bool[h,w],
+    maze_map u8[h+8,w+8,3], time i32[], terminal bool[], task_id i32[]; any leading batch dims."""
+    agent_pos: Any
+    agent_dir: Any
+    agent_dir_idx: Any
+    agent_inv: Any
+    goal_pos: Any
+    pot_pos: Any
+    wall_map: Any
+    maze_map: Any
+    time: Any
+    terminal: Any
+    task_id: Any
+
+    def replace(self, **kw):
+        return dataclasses.replace(self, **kw)
+
+    def clone(self):
+        return State(**{f.name: getattr(self, f.name).clone() for f in dataclasses.fields(self)})
+
+
+_STATE_DTYPES = {"agent_pos": torch.uint32, "agent_dir": torch.int8, "agent_dir_idx": torch.int32,
+                 "agent_inv": torch.int32, "goal_pos": torch.uint32, "pot_pos": torch.uint32,
+                 "wall_map": torch.bool, "maze_map": torch.uint8, "time": torch.int32, "terminal": torch.bool,
+                 "task_id": torch.int32}
+
+
+class Discrete:
+    """jax_marl/environments/spaces.py:19-44 (metadata only)."""
+
+    def __init__(self, num_categories, dtype=torch.int32):
+        self.n = num_categories
+        self.shape = ()
+        self.dtype = dtype
+
+
+class Box:
+    """jax_marl/environments/spaces.py:71-... (metadata only)."""
+
+    def __init__(self, low, high, shape, dtype=torch.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Overcooked:
+    """Vanilla Overcooked (overcooked.py:69), batched natively on one CUDA device."""
+
+    def __init__(self, layout=None, layout_name="cramped_room", random_reset=False, max_steps=400, task_id=0,
+                 *, device=None, prng_impl="threefry_legacy"):
+        if layout is None:   # the reference dereferences layout before its own fallback (overcooked.py:84,89)
+            layout = overcooked_layouts["cramped_room"]
+        if not torch.cuda.is_available():
+            raise _lib.OcError("jaxovercooked_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.height = int(layout["height"])
+        self.width = int(layout["width"])
+        self.obs_shape = (self.width, self.height, N_CHANNELS)   # sic: (W, H, 26); arrays are (H, W, 26)
+        self.agent_view_size = 5
+        self.layout = layout
+        self.layout_name = layout_name
+        self.agents = ["agent_0", "agent_1"]
+        self.num_agents = 2
+        self.action_set = torch.tensor([a.value for a in list(Actions)[:6]], dtype=torch.int32)
+        self.random_reset = bool(random_reset)
+        self.max_steps = int(max_steps)
+        self.task_id = int(task_id)
+        if prng_impl not in ("threefry_legacy", "threefry_partitionable"):
+            raise ValueError("prng_impl must be 'threefry_legacy' (jax < 0.5 default) or 'threefry_partitionable'")
+        self.prng_mode = _lib.PRNG_LEGACY if prng_impl == "threefry_legacy" else _lib.PRNG_PARTITIONABLE
+
+        lib = _lib.load()
+        self._keep = {f: np.ascontiguousarray(np.asarray(layout[f], dtype=np.int32).reshape(-1)) for f in LAYOUT_FIELDS}
+        if self._keep["agent_idx"].size != 2:
+            raise ValueError("layout['agent_idx'] must hold exactly two cells")
+        d = _lib.LayoutDesc()
+        d.height, d.width = self.height, self.width
+        d.n_wall = self._keep["wall_idx"].size
+        d.n_goal = self._keep["goal_idx"].size
+        d.n_pot = self._keep["pot_idx"].size
+        d.n_onion_pile = self._keep["onion_pile_idx"].size
+        d.n_plate_pile = self._keep["plate_pile_idx"].size
+        for f in LAYOUT_FIELDS:
+            setattr(d, f, self._keep[f].ctypes.data_as(C.POINTER(C.c_int32)))
+        d.random_reset, d.max_steps, d.task_id, d.prng_mode = int(self.random_reset), self.max_steps, self.task_id, self.prng_mode
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.oc_layout_create(C.byref(d), C.byref(handle)), "oc_layout_create")
+        self._handle = handle
+        self._lib = lib
+        info = _lib.LayoutInfo()
+        _lib.check(lib.oc_layout_query(handle, C.byref(info)), "oc_layout_query")
+        self.info = info
+        self.n_goal, self.n_pot = int(info.n_goal), int(info.n_pot)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                self._lib.oc_layout_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # ------------------------------------------------------------------ shapes / buffers
+    def state_shapes(self, batch=()):
+        h, w, G, P = self.height, self.width, self.n_goal, self.n_pot
+        b = tuple(batch)
+        return {"agent_pos": b + (2, 2), "agent_dir": b + (2, 2), "agent_dir_idx": b + (2,), "agent_inv": b + (2,),
+                "goal_pos": b + (G, 2), "pot_pos": b + (P, 2), "wall_map": b + (h, w),
+                "maze_map": b + (h + 2 * PAD, w + 2 * PAD, 3), "time": b, "terminal": b, "task_id": b}
+
+    def empty_state(self, batch=()):
+        return State(**{k: torch.empty(s, dtype=_STATE_DTYPES[k], device=self.device)
+                        for k, s in self.state_shapes(batch).items()})
+
+    def _state_ptrs(self, st, batch):
+        shapes = self.state_shapes(batch)
+        sp = _lib.StatePtrs()
+        for f in _lib.STATE_FIELDS:
+            t = getattr(st, f)
+            if t.dtype != _STATE_DTYPES[f] or tuple(t.shape) != shapes[f] or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"State.{f}: expected contiguous {_STATE_DTYPES[f]}{list(shapes[f])} on {self.device}, "
+                                 f"got {t.dtype}{list(t.shape)} on {t.device}")
+            setattr(sp, f, t.data_ptr())
+        return sp
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _key(self, key):
+        if key.dtype != torch.uint32 or key.shape[-1] != 2 or key.device != self.device:
+            raise ValueError("key must be a uint32 CUDA tensor of shape [..., 2] (raw threefry key data)")
+        return key.contiguous()
+
+    def _obs_buffers(self, batch):
+        shp = tuple(batch) + (self.height, self.width, N_CHANNELS)
+        return (torch.empty(shp, dtype=torch.uint8, device=self.device),
+                torch.empty(shp, dtype=torch.uint8, device=self.device))
+
+    # ------------------------------------------------------------------ the reference's three calls
+    def reset(self, key):
+        """obs, state = env.reset(key)   (overcooked.py:136-248).  key: u32[..., 2]."""
+        key = self._key(key)
+        batch = tuple(key.shape[:-1])
+        n = int(np.prod(batch)) if batch else 1
+        st = self.empty_state(batch)
+        obs0, obs1 = self._obs_buffers(batch)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.oc_reset(self._handle, n, key.data_ptr(), self._state_ptrs(st, batch),
+                                          obs0.data_ptr(), obs1.data_ptr(), self._stream()), "oc_reset")
+        return {"agent_0": obs0, "agent_1": obs1}, st
+
+    def step(self, key, state, actions, reset_state=None, *, donate=False, out=None, log=None, stats=None):
+        """obs, state, rewards, dones, infos = env.step(key, state, actions[, reset_state])
+        (multi_agent_env.py:41-69: split key, step_env, auto-reset on done).
+
+        donate=True updates `state`'s tensors in place and returns the same State (what XLA does for a donated
+        scan carry); the default allocates a fresh State.  `out` may carry preallocated result tensors
+        ({"obs0","obs1","reward","shaped0","shaped1","done"}); `log` / `stats` are used by LogWrapper."""
+        key = self._key(key)
+        batch = tuple(key.shape[:-1])
+        n = int(np.prod(batch)) if batch else 1
+        a0 = self._action(actions["agent_0"], batch)
+        a1 = self._action(actions["agent_1"], batch)
+        sp_in = self._state_ptrs(state, batch)
+        if donate:
+            new_state, sp_out = state, sp_in
+        else:
+            new_state = self.empty_state(batch)
+            sp_out = self._state_ptrs(new_state, batch)
+        rs = None
+        if reset_state is not None:
+            rs = C.byref(self._state_ptrs(reset_state, batch))
+        if out is None:
+            obs0, obs1 = self._obs_buffers(batch)
+            reward = torch.empty(batch, dtype=torch.float32, device=self.device)
+            sh0 = torch.empty(batch, dtype=torch.float32, device=self.device)
+            sh1 = torch.empty(batch, dtype=torch.float32, device=self.device)
+            done = torch.empty(batch, dtype=torch.bool, device=self.device)
+        else:
+            obs0, obs1, reward, sh0, sh1, done = (out[k] for k in ("obs0", "obs1", "reward", "shaped0", "shaped1", "done"))
+        ex = None
+        if log is not None or stats is not None:
+            e = _lib.StepExtras()
+            if log is not None:
+                for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths",
+                          "returned_episode"):
+                    setattr(e, f, _ptr(log.get(f)))
+            if stats is not None:
+                e.stats = stats.data_ptr()
+            ex = C.byref(e)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.oc_step(self._handle, n, key.data_ptr(), sp_in, a0.data_ptr(), a1.data_ptr(), rs,
+                                         sp_out, obs0.data_ptr(), obs1.data_ptr(), reward.data_ptr(), sh0.data_ptr(),
+                                         sh1.data_ptr(), done.data_ptr(), ex, self._stream()), "oc_step")
+        obs = {"agent_0": obs0, "agent_1": obs1}
+        rewards = {"agent_0": reward, "agent_1": reward}                       # overcooked.py:124
+        dones = {"agent_0": done, "agent_1": done, "__all__": done}            # :126
+        infos = {"shaped_reward": {"agent_0": sh0, "agent_1": sh1}}            # :125, :133
+        return obs, new_state, rewards, dones, infos
+
+    def get_obs(self, state):
+        """overcooked.py:250-364."""
+        batch = tuple(state.time.shape)
+        n = int(np.prod(batch)) if batch else 1
+        obs0, obs1 = self._obs_buffers(batch)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.oc_get_obs(self._handle, n, self._state_ptrs(state, batch), obs0.data_ptr(),
+                                            obs1.data_ptr(), self._stream()), "oc_get_obs")
+        return {"agent_0": obs0, "agent_1": obs1}
+
+    def _action(self, a, batch):
+        if not torch.is_tensor(a):
+            a = torch.as_tensor(a, dtype=torch.int32, device=self.device)
+        if a.dtype != torch.int32:
+            a = a.to(torch.int32)
+        if a.device != self.device:
+            a = a.to(self.device, non_blocking=True)
+        if tuple(a.shape) != tuple(batch):
+            raise ValueError(f"action shape {tuple(a.shape)} does not match the key batch {tuple(batch)}")
+        return a.contiguous()
+
+    # ------------------------------------------------------------------ metadata the callers read
+    def is_terminal(self, state):
+        return (state.time >= self.max_steps) | state.terminal                 # overcooked.py:644-647
+
+    @property
+    def name(self):
+        return self.layout_name
+
+    @property
+    def num_actions(self):
+        return len(self.action_set)
+
+    def action_space(self, agent_id=""):
+        return Discrete(len(self.action_set), dtype=torch.uint32)
+
+    def observation_space(self, agent_id=""):
+        return Box(0, 255, self.obs_shape)
+
+    def state_space(self):
+        h, w, v = self.height, self.width, self.agent_view_size
+        return {"agent_pos": Box(0, max(w, h), (2,), torch.uint32), "agent_dir": Discrete(4),
+                "goal_pos": Box(0, max(w, h), (2,), torch.uint32),
+                "maze_map": Box(0, 255, (w + v, h + v, 3), torch.uint32),
+                "time": Discrete(self.max_steps), "terminal": Discrete(2)}
+
+
+registered_envs = ["overcooked"]
+
+
+def make(env_id, **env_kwargs):
+    """jax_marl/registration.py:5-28 for the one environment family in scope."""
+    if env_id not in registered_envs:
+        raise ValueError(f"{env_id} is not in registered jaxmarl environments.")
+    return Overcooked(**env_kwargs)
+
+
+def vmap(fn, in_axes=0, out_axes=0):
+    """Stand-in for `jax.vmap` at the reference's call sites: the env methods are already batched over leading
+    dimensions, so mapping over axis 0 of every argument is the function itself."""
+    axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,)
+    if any(a != 0 for a in axes) or out_axes != 0:
+        raise NotImplementedError("only in_axes=0 / out_axes=0 (the reference's usage) is supported")
+    return fn

@@ -1,0 +1,35 @@
+"""The slice of `jax.random` the callers of the env use, on the device: PRNGKey and split.
+
+`split` runs the threefry2x32 kernel behind `oc_prng_split` (include/oc_b200.h); keys are raw uint32[2] CUDA
+tensors as in JAX's legacy key representation.  Callers' recipe (baselines/IPPO_CL.py:477,535):
+    rng, _rng = split(rng);  step_keys = split(_rng, num_envs)
+`split(key, num, first=a, count=b)` returns rows [a, a+b) only -- a GPU that owns that shard of a global batch
+of `num` environments gets exactly the keys the single-device program would use for them."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_MODES = {"threefry_legacy": _lib.PRNG_LEGACY, "threefry_partitionable": _lib.PRNG_PARTITIONABLE}
+
+
+def PRNGKey(seed, device=None):
+    """jax.random.PRNGKey(seed) with x64 disabled: [0, seed mod 2**32]."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    t = torch.tensor([0, int(seed) & 0xFFFFFFFF], dtype=torch.int64)
+    return t.to(torch.uint32).to(dev)
+
+
+def split(key, num=2, *, first=0, count=None, impl="threefry_legacy", out=None):
+    if key.dtype != torch.uint32 or tuple(key.shape) != (2,) or not key.is_cuda:
+        raise ValueError("key must be a uint32 CUDA tensor of shape [2]")
+    count = num - first if count is None else count
+    key = key.contiguous()
+    if out is None:
+        out = torch.empty((count, 2), dtype=torch.uint32, device=key.device)
+    lib = _lib.load()
+    with torch.cuda.device(key.device):
+        _lib.check(lib.oc_prng_split(_MODES[impl], key.data_ptr(), num, first, count, out.data_ptr(),
+                                     C.c_void_p(torch.cuda.current_stream(key.device).cuda_stream)), "oc_prng_split")
+    return out

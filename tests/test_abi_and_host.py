@@ -1,0 +1,94 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/oc_b200.h declares; host-side layout
+logic (registry, grid parser, padding) matches the reference-derived expectations.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    hdr = open(os.path.join(ROOT, "include", "oc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(oc_[a-z_0-9]+)\s*\(", hdr))
+    assert {"oc_reset", "oc_step", "oc_get_obs", "oc_layout_create", "oc_prng_split"} <= declared
+    lib = ctypes.CDLL(os.path.join(ROOT, "jaxovercooked_b200", "liboc_b200.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"liboc_b200.so does not export {name}"
+    lib.oc_version.restype = ctypes.c_int
+    assert lib.oc_version() == 100
+    lib.oc_status_string.restype = ctypes.c_char_p
+    assert lib.oc_status_string(-2) == b"unsupported layout"
+
+
+def test_binding_covers_header():
+    from jaxovercooked_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "oc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(oc_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    lib = _lib.load()
+    assert lib.oc_version() == 100
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    import jaxovercooked_b200 as ocb
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(Exception):
+        ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "jaxovercooked_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle/"
+
+
+def test_registry_and_padding():
+    from jaxovercooked_b200.layouts import overcooked_layouts, cl_sequence_padded, layout_grid_to_dict
+    assert len(overcooked_layouts) == 38
+    cr = overcooked_layouts["cramped_room"]
+    assert (cr["height"], cr["width"]) == (4, 5) and cr["agent_idx"].tolist() == [6, 8] and cr["pot_idx"].tolist() == [2]
+    assert overcooked_layouts["forced_coord"]["agent_idx"].tolist() == [11, 8]      # order matters: agent_0 first
+    # SURVEY.md App. C.2 (derived from baselines/IPPO_CL.py:182-278)
+    exp = {"cramped_room": ([12, 14], [4], [32], [11, 15], [30]),
+           "asymm_advantages": ([29, 32], [22, 31], [12, 17], [9, 14], [39, 41]),
+           "coord_ring": ([13, 21], [5, 15], [40], [29, 39], [20]),
+           "forced_coord": ([21, 14], [5, 15], [41], [11, 20], [29]),
+           "counter_circuit": ([11, 33], [3, 4], [25], [39, 40], [18])}
+    for name, lay in cl_sequence_padded().items():
+        assert (lay["height"], lay["width"]) == (5, 9)
+        got = tuple(lay[k].tolist() for k in ("agent_idx", "pot_idx", "goal_idx", "onion_pile_idx", "plate_pile_idx"))
+        assert got == exp[name], name
+        walls = set(lay["wall_idx"].tolist())
+        border = [i for i in range(45) if i // 9 in (0, 4) or i % 9 in (0, 8)]
+        assert all(b in walls for b in border)
+    g = layout_grid_to_dict("\nWWPWW\nOA AO\nW   W\nWBWXW\n")
+    for k in ("agent_idx", "goal_idx", "plate_pile_idx", "onion_pile_idx", "pot_idx"):
+        assert g[k].tolist() == cr[k].tolist()
+    assert sorted(set(g["wall_idx"].tolist())) == sorted(cr["wall_idx"].tolist())
+
+
+def test_all_registered_layouts_satisfy_the_abi_contract():
+    """oc_layout_create's preconditions (enclosed grid, specials on walls, two free agent cells) hold for the registry."""
+    from jaxovercooked_b200.layouts import overcooked_layouts
+    for name, l in overcooked_layouts.items():
+        h, w = l["height"], l["width"]
+        walls = set(l["wall_idx"].tolist())
+        assert h <= 16 and w <= 16 and len(l["pot_idx"]) >= 1
+        for i in range(h * w):
+            if i // w in (0, h - 1) or i % w in (0, w - 1):
+                assert i in walls, (name, i)
+        for k in ("goal_idx", "pot_idx", "onion_pile_idx", "plate_pile_idx"):
+            assert all(int(i) in walls for i in l[k]), (name, k)
+        assert len(l["agent_idx"]) == 2 and all(int(i) not in walls for i in l["agent_idx"])
