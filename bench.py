@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched Overcooked step on B200, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   the reference's algorithm on the host cores (oracle)
+    torchrun ... bench.py --gpus N ...                        one rank per GPU, env axis sharded, no per-step comms
+
+A "step" is one pass of the hot path (split key -> step_env -> auto-reset -> both observations) over one batch
+of `--envs` environments per GPU with synthetic uniform-random actions.  Workload = BASELINE.json configs[1]:
+cramped_room, 65,536 envs per GPU.  One JSON line is printed by rank 0.
+
+Timing hygiene: W >= 3 warm-up steps; `--rotate` independent env batches (state) and 8 observation slots are
+used round-robin so consecutive steps never touch the same lines and the per-cycle working set exceeds the
+126 MB L2; the timed region is a replayed CUDA graph (one kernel launch per step) bracketed by barrier +
+synchronize, timed with CUDA events on the launching stream, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "env-steps/sec (agent-pairs)"
+UNIT = "env-steps/s"
+OBS_SLOTS = 8
+GRAPH_STEPS = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="cramped_room")
+    ap.add_argument("--padded-cl", action="store_true", help="use the 5x9-padded CL version of --layout")
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--rotate", type=int, default=4, help="independent env batches stepped round-robin")
+    ap.add_argument("--random-reset", action="store_true")
+    ap.add_argument("--max-steps", type=int, default=400)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=300)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
+    return ap.parse_args()
+
+
+def get_layout(args):
+    from jaxovercooked_b200.layouts import overcooked_layouts, cl_sequence_padded
+    if args.padded_cl:
+        return cl_sequence_padded()[args.layout]
+    return overcooked_layouts[args.layout]
+
+
+def workload_name(args, lay):
+    return (f"{args.layout}{' (padded 5x9)' if args.padded_cl else ''} random-action env step, "
+            f"{args.envs} envs per GPU, grid {lay['height']}x{lay['width']}, max_steps {args.max_steps}, "
+            f"random_reset={bool(args.random_reset)}")
+
+
+def alg_bytes(lay):
+    """both obs written (52 hw) + interior of maze_map r/w (6 hw) + dynamic fields r/w (82)
+    + key/actions in, reward/shaped/dones out (35)."""
+    return 58 * int(lay["height"]) * int(lay["width"]) + 117
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic(layout_name):
+    """dram bytes per launch from the committed ncu --set full capture, if there is one for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        return t.get(layout_name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_rate(lay, args, n_envs, seconds, threads=None, steps=None):
+    """env-steps/s of the oracle (OpenMP over envs) on the host cores."""
+    from oracle import oracle as orc
+    if threads:
+        orc.set_threads(threads)
+    cores = threads or orc.max_threads()
+    o = orc.Oracle(lay, random_reset=args.random_reset, max_steps=args.max_steps)
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 2**32, (n_envs, 2), dtype=np.uint32)
+    _, st = o.reset(keys)
+    out = o.alloc_out(n_envs)
+    acts = rng.integers(0, 6, (16, n_envs, 2)).astype(np.int32)
+    a0 = [np.ascontiguousarray(acts[i, :, 0]) for i in range(16)]
+    a1 = [np.ascontiguousarray(acts[i, :, 1]) for i in range(16)]
+    for i in range(3):
+        o.step(keys, st, a0[i], a1[i], out=out)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        o.step(keys, st, a0[n % 16], a1[n % 16], out=out)
+        n += 1
+        if steps is not None:
+            if n >= steps:
+                break
+        elif time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return n_envs * n / dt, cores, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    lay = get_layout(args)
+    cores = orc.max_threads()
+    # bounded sample: size each step so that warmup + K steps finish in about a minute
+    probe, _, _, _ = cpu_rate(lay, args, 8192, 1.0)
+    budget = 60.0
+    n_envs = int(min(args.envs, max(256, probe * budget / max(1, args.steps + args.warmup))))
+    n_envs = max(256, (n_envs // 256) * 256)
+    o = orc.Oracle(lay, random_reset=args.random_reset, max_steps=args.max_steps)
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 2**32, (n_envs, 2), dtype=np.uint32)
+    _, st = o.reset(keys)
+    out = o.alloc_out(n_envs)
+    acts = rng.integers(0, 6, (16, n_envs, 2)).astype(np.int32)
+    a0 = [np.ascontiguousarray(acts[i, :, 0]) for i in range(16)]
+    a1 = [np.ascontiguousarray(acts[i, :, 1]) for i in range(16)]
+    for i in range(max(3, args.warmup)):
+        o.step(keys, st, a0[i % 16], a1[i % 16], out=out)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o.step(keys, st, a0[i % 16], a1[i % 16], out=out)
+    dt = time.perf_counter() - t0
+    value = n_envs * args.steps / dt
+    sample = (f"{n_envs} of {args.envs} envs per step x {args.steps} steps, C restatement of the reference "
+              f"(oracle/oc_oracle.c, OpenMP, {cores} threads); the reference's own JAX path cannot be installed here")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args, lay), "sample_envs_per_step": n_envs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:   # CUDA_VISIBLE_DEVICES may renumber: resolve the CUDA device through its UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                     "applications_clocks": 0x2}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        if self._th is not None:
+            self._stop.set()
+            self._th.join()
+        if self.nv is not None and not self.samples:
+            self._once()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import jaxovercooked_b200 as ocb
+    from jaxovercooked_b200 import random as ocr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    lay = get_layout(args)
+    N, R = args.envs, max(1, args.rotate)
+    n_global = N * world
+    first = rank * N
+    env = ocb.make("overcooked", layout=lay, random_reset=args.random_reset, max_steps=args.max_steps)
+    wenv = ocb.LogWrapper(env) if args.log_wrapper else env
+    h, w = env.height, env.width
+    B_alg = alg_bytes(lay)
+
+    # R independent env batches (different seeds), sharded by GLOBAL env index: same trajectories for any world size
+    rngs, states = [], []
+    for b in range(R):
+        rng = ocr.PRNGKey(b)
+        ks = ocr.split(rng, 2)
+        rngs.append(ks[0].clone())
+        _, st = wenv.reset(ocr.split(ks[1], n_global, first=first, count=N))
+        states.append(st)
+    outs = [{"obs0": torch.empty((N, h, w, 26), dtype=torch.uint8, device=dev),
+             "obs1": torch.empty((N, h, w, 26), dtype=torch.uint8, device=dev),
+             "reward": torch.empty(N, dtype=torch.float32, device=dev),
+             "shaped0": torch.empty(N, dtype=torch.float32, device=dev),
+             "shaped1": torch.empty(N, dtype=torch.float32, device=dev),
+             "done": torch.empty(N, dtype=torch.bool, device=dev)} for _ in range(OBS_SLOTS)]
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    n_act = 16
+    acts = [{"agent_0": torch.randint(0, 6, (N,), dtype=torch.int32, device=dev, generator=g),
+             "agent_1": torch.randint(0, 6, (N,), dtype=torch.int32, device=dev, generator=g)} for _ in range(n_act)]
+    stats = torch.zeros(8, dtype=torch.int64, device=dev) if args.log_wrapper else None
+
+    # per-step subkeys: the callers' `rng, _rng = split(rng)` chain, refreshed for GRAPH_STEPS steps at a time;
+    # the per-env `split(_rng, num_envs)` is fused into the step kernel (LazySplit)
+    subkeys = torch.zeros((GRAPH_STEPS, 2), dtype=torch.uint32, device=dev)
+    from jaxovercooked_b200 import _lib as oclib
+    import ctypes as C
+    lib = oclib.load()
+    chain_rng = rngs[0]
+
+    def launch_chain():
+        oclib.check(lib.oc_prng_chain(env.prng_mode, chain_rng.data_ptr(), GRAPH_STEPS, subkeys.data_ptr(),
+                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "oc_prng_chain")
+
+    def one_step(i):
+        b, slot = i % R, i % OBS_SLOTS
+        key = ocr.LazySplit(subkeys[i % GRAPH_STEPS], n_global, first, N)
+        kw = dict(donate=True, out=outs[slot])
+        if args.log_wrapper:
+            kw["stats"] = stats
+        _, states[b], _, _, _ = wenv.step(key, states[b], acts[i % n_act], **kw)
+
+    def block(n_blocks):
+        for _ in range(n_blocks):
+            launch_chain()
+            for i in range(GRAPH_STEPS):
+                one_step(i)
+
+    K = max(GRAPH_STEPS, (args.steps // GRAPH_STEPS) * GRAPH_STEPS)
+    Wm = max(3, args.warmup)
+    n_warm_blocks = (Wm + GRAPH_STEPS - 1) // GRAPH_STEPS
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        block(1)                      # eager once (sets function attributes, warms allocator)
+        torch.cuda.synchronize()
+        graph = None
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                block(1)
+        run_blocks = (lambda n: [graph.replay() for _ in range(n)]) if graph is not None else block
+        run_blocks(n_warm_blocks)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        run_blocks(K // GRAPH_STEPS)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        if stats is not None and world > 1:
+            dist.all_reduce(stats)     # the rollout statistics: the only collective on this path
+
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = n_global * K / (ms * 1e-3)
+    launches_per_block = GRAPH_STEPS + 1
+    gpu_launches = (K // GRAPH_STEPS) * launches_per_block
+
+    # ---- e2e: the public API with HOST buffers; H2D of the actions and D2H of rewards/shaped/dones every step
+    Ke = max(8, min(args.e2e_steps, args.steps))
+    h_act = [torch.randint(0, 6, (2, N), dtype=torch.int32).pin_memory() for _ in range(8)]
+    h_res = {k: torch.empty(N, dtype=dt).pin_memory() for k, dt in (("reward", torch.float32), ("shaped0", torch.float32),
+                                                                   ("shaped1", torch.float32), ("done", torch.bool))}
+    d_act = torch.empty((2, N), dtype=torch.int32, device=dev)
+    e_rng = rngs[1 % R]
+
+    def e2e_step(i):
+        b, slot = i % R, i % OBS_SLOTS
+        d_act.copy_(h_act[i % 8], non_blocking=True)
+        ks = ocr.split(e_rng, 2)
+        e_rng.copy_(ks[0])
+        key = ocr.LazySplit(ks[1], n_global, first, N)
+        _, states[b], rew, done, info = env.step(key, states[b].env_state if args.log_wrapper else states[b],
+                                                 {"agent_0": d_act[0], "agent_1": d_act[1]}, donate=True, out=outs[slot])
+        h_res["reward"].copy_(rew["agent_0"], non_blocking=True)
+        h_res["shaped0"].copy_(info["shaped_reward"]["agent_0"], non_blocking=True)
+        h_res["shaped1"].copy_(info["shaped_reward"]["agent_1"], non_blocking=True)
+        h_res["done"].copy_(done["__all__"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the step's result before acting again
+
+    e2e = None
+    if not args.log_wrapper:
+        for i in range(5):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_global * Ke / float(tm.item()), "unit": UNIT, "h2d_bytes_per_step": 8 * N,
+               "d2h_bytes_per_step": 13 * N, "steps": Ke,
+               "note": "env.step through the host mirror/C ABI; actions from pinned host memory, rewards+shaped+dones "
+                       "read back every step; observations stay on the device for the learner, as in the reference"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    step_s = ms * 1e-3 / K
+    achieved = B_alg * N / step_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(args.layout), "kernel": "oc_env_kernel<MODE_STEP>",
+                "algorithmic_bytes_per_env_step": B_alg, "envs_per_launch": N, "avg_launch_us": step_s * 1e6,
+                "peak_source": peak_src}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        n_cpu = min(N, 16384)
+        v, cores, n_steps, dt = cpu_rate(lay, args, n_cpu, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} envs x {n_steps} steps in {dt:.1f} s, oracle/oc_oracle.c (C restatement, OpenMP); "
+                         "the reference's JAX CPU path is not installable in this image"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": n_warm_blocks * GRAPH_STEPS,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, lay), "envs_per_gpu": N, "global_envs": n_global,
+                       "l2": f"inputs larger than L2: {R} independent env batches + {OBS_SLOTS} observation slots "
+                             f"round-robin (state {R * N * (env.info.map_bytes_per_env + 41) / 1e6:.0f} MB + obs "
+                             f"{OBS_SLOTS * 2 * N * h * w * 26 / 1e6:.0f} MB per cycle vs 126 MB L2)",
+                       "launch": "CUDA graph of 8 steps replayed" if graph is not None else "eager launches",
+                       "keys": "per-step subkeys from the split chain; per-env split fused in the kernel",
+                       "log_wrapper": bool(args.log_wrapper), "parallelism": f"env-sharded x{world}, no per-step comms"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
+    if stats is not None:
+        line["stats"] = stats.cpu().tolist()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__ as ge
+        if not os.path.exists(ge.LIB):
+            ge.build()
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

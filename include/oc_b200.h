@@ -13,8 +13,10 @@
  * batched over the leading N; see INTEGRATION.md for the binding stubs.
  *
  * Conventions
- *   - every data pointer is a DEVICE pointer owned by the caller, 16-byte aligned at its base, valid until
- *     `stream` reaches the call; nothing here allocates per call, synchronises, throws or exits;
+ *   - every data pointer is a DEVICE pointer owned by the caller, valid until `stream` reaches the call, and
+ *     naturally aligned for its element type (agent_pos: 8 bytes -- it is read as (x,y) pairs); observation
+ *     buffers that are 16-byte aligned leave the SM through the bulk-copy engine, others through a slower
+ *     plain-store path; nothing here allocates per call, synchronises, throws or exits;
  *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
  *   - return value: OC_OK or a negative oc_status; oc_status_string() names it;
  *   - an oc_layout is an immutable handle (host struct + a small device-side descriptor on the CUDA device
@@ -43,7 +45,7 @@ typedef enum {
     OC_ERR_INVALID_ARG = -1,         /* NULL pointer, N < 0, bad enum */
     OC_ERR_UNSUPPORTED_LAYOUT = -2,  /* see oc_layout_create */
     OC_ERR_CUDA = -3,                /* a CUDA runtime call failed; cudaGetLastError has the detail */
-    OC_ERR_ALIGNMENT = -4,           /* a base pointer is not 16-byte aligned */
+    OC_ERR_ALIGNMENT = -4,           /* a pointer is not aligned for its element type */
     OC_ERR_NO_DEVICE = -5            /* no usable sm_100 device: there is NO CPU fallback */
 } oc_status;
 
@@ -100,6 +102,13 @@ typedef struct {
      * episodes, [5] sum returned_episode_lengths[:,0] over finished episodes, [6] env-steps, [7] reserved.
      * All addends are integers, so the totals are order-independent and bit-reproducible. */
     long long *stats;
+    /* Fused key derivation: when oc_step is called with keys == NULL, env i uses
+     * jax.random.split(*split_key, split_num)[split_first + i] (split_key: DEVICE u32[2]), evaluated in the
+     * kernel and only for environments that reset -- the callers' `split(_rng, num_envs)`
+     * (baselines/IPPO_CL.py:535) without materialising or reading the [N,2] key array. */
+    const uint32_t *split_key;
+    int64_t split_num;
+    int64_t split_first;
 } oc_step_extras;
 
 typedef struct {
@@ -127,6 +136,7 @@ int oc_reset(const oc_layout *layout, int64_t N, const uint32_t *keys, oc_state 
 
 /* env.step under vmap: multi_agent_env.py:41-69 -> overcooked.py:106-134 (step_env), :366-514 (step_agents),
  * :516-642 (process_interact), :250-364 (get_obs), with auto-reset from `split(key)[1]`.
+ *   keys          u32[N,2] per-env keys, or NULL with extras->split_key set (fused split, see oc_step_extras)
  *   act0/act1     i32[N], values 0..5 (overcooked.py:93-100)
  *   reset_state   NULL, or the caller-supplied `reset_state` of multi_agent_env.py:47,55-59
  *   out           may alias `in` field by field (the fast path: XLA input_output_aliases / donated scan
@@ -149,6 +159,11 @@ int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, u
  * `num` derives exactly the keys the single-device program would. */
 int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first, int64_t count,
                   uint32_t *out, void *stream);
+
+/* n sequential `key, sub = jax.random.split(key)` on the device (the callers' per-step
+ * `rng, _rng = jax.random.split(rng)`, IPPO_CL.py:533): subkeys u32[n,2] receives the n `sub`s and *key (DEVICE
+ * u32[2]) is advanced in place. */
+int oc_prng_chain(int prng_mode, uint32_t *key, int n, uint32_t *subkeys, void *stream);
 
 const char *oc_status_string(int status);
 int oc_version(void);

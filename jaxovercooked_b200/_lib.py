@@ -35,7 +35,8 @@ class StatePtrs(C.Structure):
 
 
 class StepExtras(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in EXTRA_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in EXTRA_FIELDS] + [("split_key", C.c_void_p), ("split_num", C.c_int64),
+                                                          ("split_first", C.c_int64)]
 
 
 class LayoutInfo(C.Structure):
@@ -46,7 +47,7 @@ class LayoutInfo(C.Structure):
 
 
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
-           "oc_reset", "oc_step", "oc_get_obs", "oc_prng_split")
+           "oc_reset", "oc_step", "oc_get_obs", "oc_prng_split", "oc_prng_chain")
 
 _lib = None
 
@@ -86,6 +87,8 @@ def load():
                             C.c_void_p, C.c_void_p, C.POINTER(StepExtras), C.c_void_p]
     lib.oc_prng_split.restype = C.c_int
     lib.oc_prng_split.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.oc_prng_chain.restype = C.c_int
+    lib.oc_prng_chain.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -139,6 +139,20 @@ __device__ __forceinline__ int randint_at(int part, uint32_t k0, uint32_t k1, in
     return (int)(off % span);
 }
 
+// row i of jax.random.split(key, num): depends only on (key, i, num)
+__device__ __forceinline__ void split_row(int part, uint32_t k0, uint32_t k1, long long num, long long i,
+                                          uint32_t &r0, uint32_t &r1) {
+    uint32_t a, b;
+    if (part) { tf2x32(k0, k1, 0u, (uint32_t)i, r0, r1); return; }
+    // legacy: flat word j of threefry_2x32(key, iota(2*num)); the counters are split in two halves of `num`
+    long long j = 2 * i;
+    if (j < num) { tf2x32(k0, k1, (uint32_t)j, (uint32_t)(j + num), a, b); r0 = a; }
+    else { tf2x32(k0, k1, (uint32_t)(j - num), (uint32_t)j, a, b); r0 = b; }
+    j += 1;
+    if (j < num) { tf2x32(k0, k1, (uint32_t)j, (uint32_t)(j + num), a, b); r1 = a; }
+    else { tf2x32(k0, k1, (uint32_t)(j - num), (uint32_t)j, a, b); r1 = b; }
+}
+
 // ------------------------------------------------------------------------------------------ small helpers
 
 __device__ __forceinline__ unsigned fastdiv(unsigned x, unsigned magic) { return __umulhi(x, magic); }
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         unsigned char *my_span = smap + es * span_stride + shift_lane;
 
         // ---------------------------------------------------------------- (1) stage the interior spans
-        if (MODE != MODE_RESET) {
+        {   // (oc_reset: the pre-pass has already written the template, so partial edge words hold ring bytes)
             const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map);
             const int total = n_valid * span_words;
             for (int f = lane; f < total; f += 32) {
@@ -346,7 +360,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
                     }
                     __syncwarp();
                     if (done && active) {
-                        uint32_t k0 = __ldg(p.keys + env * 2), k1 = __ldg(p.keys + env * 2 + 1);
+                        uint32_t k0, k1;
+                        if (p.keys) { k0 = __ldg(p.keys + env * 2); k1 = __ldg(p.keys + env * 2 + 1); }
+                        else {   // the caller's split(key, num_envs) fused in: derive this env's row on demand
+                            split_row(part, __ldg(p.ex.split_key), __ldg(p.ex.split_key + 1), p.ex.split_num,
+                                      p.ex.split_first + env, k0, k1);
+                        }
                         uint32_t s0, s1;
                         if (MODE == MODE_STEP) { split2(part, k0, k1, s0, s1); k0 = s0; k1 = s1; }   // key_reset
                         uint32_t a0, a1, d0, d1, q0, q1, i0, i1;
@@ -584,20 +603,22 @@ __global__ void oc_split_kernel(int part, const uint32_t *__restrict__ key, long
     const uint32_t k0 = __ldg(key), k1 = __ldg(key + 1);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += stride) {
-        const long long i = first + r;
         uint32_t a, b;
-        if (part) {
-            tf2x32(k0, k1, 0u, (uint32_t)i, a, b);
-            out[2 * r] = a; out[2 * r + 1] = b;
-        } else {
-            #pragma unroll
-            for (int c = 0; c < 2; ++c) {   // flat word j of threefry_2x32(key, iota(2*num)): halves of `num` blocks
-                const long long j = 2 * i + c;
-                if (j < num) { tf2x32(k0, k1, (uint32_t)j, (uint32_t)(j + num), a, b); out[2 * r + c] = a; }
-                else { tf2x32(k0, k1, (uint32_t)(j - num), (uint32_t)j, a, b); out[2 * r + c] = b; }
-            }
-        }
+        split_row(part, k0, k1, num, first + r, a, b);
+        out[2 * r] = a; out[2 * r + 1] = b;
     }
+}
+
+// n sequential `key, sub = split(key)` (the callers' per-step `rng, _rng = jax.random.split(rng)`), one thread
+__global__ void oc_chain_kernel(int part, uint32_t *__restrict__ key, int n, uint32_t *__restrict__ subs) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int i = 0; i < n; ++i) {
+        uint32_t s0, s1;
+        split2(part, k0, k1, s0, s1);
+        subs[2 * i] = s0; subs[2 * i + 1] = s1;
+    }
+    key[0] = k0; key[1] = k1;
 }
 
 }  // namespace
@@ -659,9 +680,13 @@ bool state_ok(const oc_state &s) {
            s.maze_map && s.time && s.terminal && s.task_id;
 }
 
+bool aligned_to(const void *p, unsigned a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1u)) == 0; }
+
+// what the kernels' vector accesses need: agent_pos is read as uint2, maze_map as 32-bit words, agent_dir as char2
 bool state_aligned(const oc_state &s) {
-    return aligned16(s.agent_pos) && aligned16(s.agent_dir) && aligned16(s.agent_dir_idx) && aligned16(s.agent_inv) &&
-           aligned16(s.maze_map) && aligned16(s.time);
+    return aligned_to(s.agent_pos, 8) && aligned_to(s.agent_dir, 2) && aligned_to(s.agent_dir_idx, 4) &&
+           aligned_to(s.agent_inv, 4) && aligned_to(s.maze_map, 4) && aligned_to(s.time, 4) &&
+           aligned_to(s.goal_pos, 4) && aligned_to(s.pot_pos, 4) && aligned_to(s.task_id, 4);
 }
 
 template <int MODE>
@@ -704,7 +729,7 @@ const char *oc_status_string(int s) {
         case OC_ERR_INVALID_ARG: return "invalid argument";
         case OC_ERR_UNSUPPORTED_LAYOUT: return "unsupported layout";
         case OC_ERR_CUDA: return "CUDA runtime error";
-        case OC_ERR_ALIGNMENT: return "base pointer not 16-byte aligned";
+        case OC_ERR_ALIGNMENT: return "pointer not aligned for its element type";
         case OC_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
         default: return "unknown status";
     }
@@ -862,7 +887,7 @@ int oc_reset(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state out
              void *stream_) {
     if (!lay || N < 0 || !keys || !state_ok(out) || !obs0 || !obs1) return OC_ERR_INVALID_ARG;
     if (N == 0) return OC_OK;
-    if (!state_aligned(out) || !aligned16(keys)) return OC_ERR_ALIGNMENT;
+    if (!state_aligned(out) || !aligned_to(keys, 4)) return OC_ERR_ALIGNMENT;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     long long blocks = (N * lay->host.map_bytes + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -890,12 +915,16 @@ int oc_step(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state in, 
             const int32_t *act1, const oc_state *reset_state, oc_state out, uint8_t *obs0, uint8_t *obs1,
             float *reward, float *shaped0, float *shaped1, uint8_t *done, const oc_step_extras *extras,
             void *stream_) {
-    if (!lay || N < 0 || !keys || !state_ok(in) || !state_ok(out) || !act0 || !act1 || !obs0 || !obs1 || !reward ||
+    if (!lay || N < 0 || !state_ok(in) || !state_ok(out) || !act0 || !act1 || !obs0 || !obs1 || !reward ||
         !shaped0 || !shaped1 || !done)
+        return OC_ERR_INVALID_ARG;
+    if (!keys && !(extras && extras->split_key && extras->split_num >= 1 && extras->split_first >= 0 &&
+                   extras->split_first + N <= extras->split_num && extras->split_num <= 0x7fffffffll))
         return OC_ERR_INVALID_ARG;
     if (reset_state && !state_ok(*reset_state)) return OC_ERR_INVALID_ARG;
     if (N == 0) return OC_OK;
-    if (!state_aligned(in) || !state_aligned(out) || !aligned16(keys) || !aligned16(act0) || !aligned16(act1) ||
+    if (!state_aligned(in) || !state_aligned(out) || (keys && !aligned_to(keys, 4)) || !aligned_to(act0, 4) ||
+        !aligned_to(act1, 4) || !aligned_to(reward, 4) || !aligned_to(shaped0, 4) || !aligned_to(shaped1, 4) ||
         (reset_state && !state_aligned(*reset_state)))
         return OC_ERR_ALIGNMENT;
     if (extras) {
@@ -936,6 +965,14 @@ int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first
     long long blocks = (count + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     oc_split_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(prng_mode, key, num, first, count, out);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : fail_cuda();
+}
+
+int oc_prng_chain(int prng_mode, uint32_t *key, int n, uint32_t *subkeys, void *stream_) {
+    if (!key || !subkeys || n < 0) return OC_ERR_INVALID_ARG;
+    if (prng_mode != OC_PRNG_THREEFRY_LEGACY && prng_mode != OC_PRNG_THREEFRY_PARTITIONABLE) return OC_ERR_INVALID_ARG;
+    if (n == 0) return OC_OK;
+    oc_chain_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(prng_mode, key, n, subkeys);
     return cudaGetLastError() == cudaSuccess ? OC_OK : fail_cuda();
 }
 

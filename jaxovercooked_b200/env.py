@@ -211,8 +211,14 @@ class Overcooked:
         donate=True updates `state`'s tensors in place and returns the same State (what XLA does for a donated
         scan carry); the default allocates a fresh State.  `out` may carry preallocated result tensors
         ({"obs0","obs1","reward","shaped0","shaped1","done"}); `log` / `stats` are used by LogWrapper."""
-        key = self._key(key)
-        batch = tuple(key.shape[:-1])
+        lazy = None
+        if hasattr(key, "materialize"):        # random.LazySplit: per-env keys derived inside the kernel
+            lazy, batch, key_ptr = key, (key.count,), None
+            if lazy.key.device != self.device:
+                raise ValueError("LazySplit key lives on another device")
+        else:
+            key = self._key(key)
+            batch, key_ptr = tuple(key.shape[:-1]), key.data_ptr()
         n = int(np.prod(batch)) if batch else 1
         a0 = self._action(actions["agent_0"], batch)
         a1 = self._action(actions["agent_1"], batch)
@@ -234,8 +240,10 @@ class Overcooked:
         else:
             obs0, obs1, reward, sh0, sh1, done = (out[k] for k in ("obs0", "obs1", "reward", "shaped0", "shaped1", "done"))
         ex = None
-        if log is not None or stats is not None:
+        if log is not None or stats is not None or lazy is not None:
             e = _lib.StepExtras()
+            if lazy is not None:
+                e.split_key, e.split_num, e.split_first = lazy.key.data_ptr(), lazy.num, lazy.first
             if log is not None:
                 for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths",
                           "returned_episode"):
@@ -244,7 +252,7 @@ class Overcooked:
                 e.stats = stats.data_ptr()
             ex = C.byref(e)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.oc_step(self._handle, n, key.data_ptr(), sp_in, a0.data_ptr(), a1.data_ptr(), rs,
+            _lib.check(self._lib.oc_step(self._handle, n, key_ptr, sp_in, a0.data_ptr(), a1.data_ptr(), rs,
                                          sp_out, obs0.data_ptr(), obs1.data_ptr(), reward.data_ptr(), sh0.data_ptr(),
                                          sh1.data_ptr(), done.data_ptr(), ex, self._stream()), "oc_step")
         obs = {"agent_0": obs0, "agent_1": obs1}

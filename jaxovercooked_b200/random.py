@@ -33,3 +33,35 @@ def split(key, num=2, *, first=0, count=None, impl="threefry_legacy", out=None):
         _lib.check(lib.oc_prng_split(_MODES[impl], key.data_ptr(), num, first, count, out.data_ptr(),
                                      C.c_void_p(torch.cuda.current_stream(key.device).cuda_stream)), "oc_prng_split")
     return out
+
+
+class LazySplit:
+    """`split(key, num)[first : first+count]` that is never materialised: pass it as the `key` of `env.step`
+    and the kernel derives each env's key itself, only when that env resets (oc_step_extras.split_key)."""
+
+    def __init__(self, key, num, first=0, count=None):
+        if key.dtype != torch.uint32 or tuple(key.shape) != (2,) or not key.is_cuda:
+            raise ValueError("key must be a uint32 CUDA tensor of shape [2]")
+        self.key, self.num, self.first = key, int(num), int(first)
+        self.count = self.num - self.first if count is None else int(count)
+        if self.first < 0 or self.count < 0 or self.first + self.count > self.num:
+            raise ValueError("shard [first, first+count) outside [0, num)")
+
+    @property
+    def shape(self):
+        return (self.count, 2)
+
+    def materialize(self, impl="threefry_legacy"):
+        return split(self.key, self.num, first=self.first, count=self.count, impl=impl)
+
+
+def split_chain(key, n, *, impl="threefry_legacy"):
+    """n times `key, sub = split(key)`: returns the n subkeys u32[n,2] and advances `key` IN PLACE."""
+    if key.dtype != torch.uint32 or tuple(key.shape) != (2,) or not key.is_cuda or not key.is_contiguous():
+        raise ValueError("key must be a contiguous uint32 CUDA tensor of shape [2]")
+    subs = torch.empty((n, 2), dtype=torch.uint32, device=key.device)
+    lib = _lib.load()
+    with torch.cuda.device(key.device):
+        _lib.check(lib.oc_prng_chain(_MODES[impl], key.data_ptr(), n, subs.data_ptr(),
+                                     C.c_void_p(torch.cuda.current_stream(key.device).cuda_stream)), "oc_prng_chain")
+    return subs

@@ -43,7 +43,7 @@ class LogWrapper(JaxMARLWrapper):
         return obs, LogEnvState(env_state, z(), z(), z(), z())
 
     def step(self, key, state, action, *, donate=False, out=None, stats=None):
-        batch = tuple(key.shape[:-1])
+        batch = tuple(key.shape[:-1])      # works for raw keys [..., 2] and for random.LazySplit
         if donate:
             trackers = {f: getattr(state, f) for f in ("episode_returns", "episode_lengths",
                                                         "returned_episode_returns", "returned_episode_lengths")}

@@ -202,6 +202,31 @@ def test_prng_split_matches_oracle():
         assert_same(got, full[1024:1536], f"sharded split {impl}")
 
 
+def test_lazy_split_equals_materialised_keys():
+    """keys=NULL + split_key: the kernel derives split(key, num)[first+i] itself, only for envs that reset."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    lay = ocb.overcooked_layouts["forced_coord"]
+    for impl in ("threefry_legacy", "threefry_partitionable"):
+        env = ocb.make("overcooked", layout=lay, random_reset=True, max_steps=5, prng_impl=impl)
+        num, first, N = 5000, 1234, 999
+        _, st_a = env.reset(ocr.split(ocr.PRNGKey(1), num, first=first, count=N, impl=impl))
+        st_b = st_a.clone()
+        rng = ocr.PRNGKey(2)
+        subs = ocr.split_chain(rng, 12, impl=impl)
+        ref_rng = ocr.PRNGKey(2)
+        for t in range(12):
+            ks = ocr.split(ref_rng, 2, impl=impl); ref_rng = ks[0]
+            assert torch.equal(ks[1].view(torch.int32), subs[t].view(torch.int32))
+            a = {"agent_0": torch.randint(0, 6, (N,), dtype=torch.int32, device="cuda"),
+                 "agent_1": torch.randint(0, 6, (N,), dtype=torch.int32, device="cuda")}
+            oa, st_a, *_ = env.step(ocr.split(subs[t], num, first=first, count=N, impl=impl), st_a, a, donate=True)
+            ob, st_b, *_ = env.step(ocr.LazySplit(subs[t], num, first, N), st_b, a, donate=True)
+            assert torch.equal(oa["agent_0"], ob["agent_0"]) and torch.equal(oa["agent_1"], ob["agent_1"])
+            gh.compare_state(st_b, gh.state_to_numpy(st_a), f"{impl} t={t}")
+        assert torch.equal(rng.view(torch.int32), ref_rng.view(torch.int32))
+
+
 def test_stats_accumulators_exact():
     ocb, orc, gh = _mods()
     lay = ocb.overcooked_layouts["cramped_room"]
