@@ -218,18 +218,74 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
     const int part = p.part;
     const int view_bytes = epw * C * OC_OBS_CHANNELS;
     unsigned char *wbase = smem + kHdrBytes + (size_t)warp * p.warp_bytes;
-    uint32_t *stage0 = reinterpret_cast<uint32_t *>(wbase);
-    uint32_t *stage1 = reinterpret_cast<uint32_t *>(wbase + view_bytes);
-    unsigned char *smap = wbase + 2 * view_bytes;
-    uint32_t *smap_w = reinterpret_cast<uint32_t *>(smap);
-    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap + epw * span_stride);   // [2*epw] packed agent state
+    uint32_t *stage0 = reinterpret_cast<uint32_t *>(wbase);                    // agent_0's view of the tile
+    unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride], double-buffered
+    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] packed agent state
     __syncthreads();
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
     bool bulk_pending = false;
+    // agent_1's view differs from agent_0's only in bytes 0..9 of the two agent cells (overcooked.py:356-359):
+    // both observation buffers receive the SAME staged image through the bulk-copy engine, and each lane then
+    // rewrites its own agent cell's 10 bytes in obs1 once that copy has completed (deferred to the next tile).
+    bool patch_valid = false;
+    size_t patch_off = 0;
+    int patch_code = 0;
+    auto apply_patch = [&]() {
+        if (patch_valid) {
+            const uint32_t *r = s_rec + patch_code * kRecWords;
+            const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
+            unsigned short *g = reinterpret_cast<unsigned short *>(p.obs1 + patch_off);
+            g[0] = (unsigned short)(w0 & 0xffffu); g[1] = (unsigned short)(w0 >> 16);
+            g[2] = (unsigned short)(w1 & 0xffffu); g[3] = (unsigned short)(w1 >> 16);
+            g[4] = (unsigned short)(w2 & 0xffffu);
+        }
+        patch_valid = false;
+    };
 
-    for (long long tile = (long long)blockIdx.x * kWarpsPerCta + warp; tile < p.n_tiles;
-         tile += (long long)gridDim.x * kWarpsPerCta) {
+    // cp.async (LDGSTS) of one tile's interior spans into span buffer `b`: 4-byte granular because an env's
+    // maze_map is only guaranteed 1-byte... tile-relative word alignment (map_bytes need not be a multiple of 4)
+    const long long tile_stride = (long long)gridDim.x * kWarpsPerCta;
+    auto prefetch_spans = [&](long long tl, int b) {
+        const long long e0 = tl * epw;
+        const int nv = (int)min((long long)epw, p.N - e0);
+        const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map);
+        uint32_t *dstw = reinterpret_cast<uint32_t *>(smap_buf + b * epw * span_stride);
+        const int total = nv * span_words;
+        for (int f = lane; f < total; f += 32) {
+            const int el = (int)fastdiv((unsigned)f, p.magic_sw);
+            const int k = f - el * span_words;
+            const long long gb = (e0 + el) * (long long)p.map_bytes + p.span_off;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                         :: "r"(smem_u32(dstw + el * (span_stride >> 2) + k)), "l"(mw + (gb >> 2) + k) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    struct Fields { uint2 pos; char2 dir; int di, inv, t, act; };
+    auto load_fields = [&](long long tl) {
+        Fields f;
+        f.pos = make_uint2(0u, 0u); f.dir = make_char2(0, 0); f.di = 0; f.inv = 1; f.t = 0; f.act = 4;
+        const long long e0 = tl * epw;
+        const int nv = (int)min((long long)epw, p.N - e0);
+        if (e < nv && MODE != MODE_RESET) {
+            const long long en = e0 + e;
+            f.pos = reinterpret_cast<const uint2 *>(p.st.agent_pos)[en * 2 + ai];
+            f.di = p.st.agent_dir_idx[en * 2 + ai];
+            f.inv = p.st.agent_inv[en * 2 + ai];
+            f.t = p.st.time[en];
+            if (MODE == MODE_STEP) {
+                f.dir = reinterpret_cast<const char2 *>(p.st.agent_dir)[en * 2 + ai];
+                f.act = __ldg((ai ? p.act1 : p.act0) + en);
+            }
+        }
+        return f;
+    };
+    long long tile = (long long)blockIdx.x * kWarpsPerCta + warp;
+    int buf = 0;
+    Fields nf;
+    if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
+
+    for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
         const long long env0 = tile * epw;
         const int n_valid = (int)min((long long)epw, p.N - env0);
         const bool active = e < n_valid;
@@ -238,35 +294,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         // byte offset (within maze_map) of this env's interior span, and its word misalignment
         const long long gb_lane = env * (long long)p.map_bytes + p.span_off;
         const int shift_lane = (int)(gb_lane & 3);
+        unsigned char *smap = smap_buf + buf * epw * span_stride;
+        uint32_t *smap_w = reinterpret_cast<uint32_t *>(smap);
         unsigned char *my_span = smap + es * span_stride + shift_lane;
 
-        // ---------------------------------------------------------------- (1) stage the interior spans
-        {   // (oc_reset: the pre-pass has already written the template, so partial edge words hold ring bytes)
-            const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map);
-            const int total = n_valid * span_words;
-            for (int f = lane; f < total; f += 32) {
-                const int el = (int)fastdiv((unsigned)f, p.magic_sw);
-                const int k = f - el * span_words;
-                const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
-                smap_w[el * (span_stride >> 2) + k] = mw[(gb >> 2) + k];   // plain load: rewritten in place below
-            }
+        // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
+        const Fields cf = nf;
+        if (tile + tile_stride < p.n_tiles) {
+            prefetch_spans(tile + tile_stride, buf ^ 1);
+            nf = load_fields(tile + tile_stride);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-
-        // ---------------------------------------------------------------- (2) per-agent state
-        int px = 0, py = 0, dx = 0, dy = 0, di = 0, inv = 1, act = 4, t = 0;
-        if (active && MODE != MODE_RESET) {
-            const uint2 pp = reinterpret_cast<const uint2 *>(p.st.agent_pos)[env * 2 + ai];
-            px = (int)pp.x; py = (int)pp.y;
-            di = p.st.agent_dir_idx[env * 2 + ai];
-            inv = p.st.agent_inv[env * 2 + ai];
-            t = p.st.time[env];
-            if (MODE == MODE_STEP) {
-                const char2 dd = reinterpret_cast<const char2 *>(p.st.agent_dir)[env * 2 + ai];
-                dx = dd.x; dy = dd.y;
-                act = __ldg((ai ? p.act1 : p.act0) + env);
-                act = clampi(act, 0, 5);
-            }
-        }
+        const int px = (int)cf.pos.x, py = (int)cf.pos.y, dx = cf.dir.x, dy = cf.dir.y, di = cf.di, inv = cf.inv, t = cf.t;
+        const int act = clampi(cf.act, 0, 5);
         __syncwarp();
 
         int nx = px, ny = py, ndi = di, ninv = inv, t_out = t, term_out = 0;
@@ -426,19 +468,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
             if (active)
                 s_ap[lane] = (uint32_t)nx | ((uint32_t)ny << 4) | ((uint32_t)ndi << 8) | ((uint32_t)inv_code(ninv) << 10) |
                              ((uint32_t)urg << 12);
-            if (bulk_pending) {   // the previous tile's bulk copies must have finished READING the staging buffers
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (bulk_pending) {   // the previous tile's bulk copies must be COMPLETE: staging is reused, obs1 is patched
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 bulk_pending = false;
+                __syncwarp();
+                apply_patch();
             }
             __syncwarp();
             const int n_cells = n_valid * C;
             const int n_pairs = (n_cells + 1) >> 1;
             for (int q = lane; q < n_pairs; q += 32) {
-                uint32_t rA0[8], rB0[8], rA1[8], rB1[8];
+                uint32_t rA[8], rB[8];
                 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int g = 2 * q + u;
-                    int code0 = 0, code1 = 0;
+                    int code0 = 0;
                     uint32_t urgbit = 0;
                     if (g < n_cells) {
                         const int el = (int)fastdiv((unsigned)g, p.magic_C);
@@ -451,33 +495,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
                         urgbit = (ap0 >> 12) & 1u;
                         if ((ap0 & 0xffu) == xy) {            // :313-319 agent cells show the inventory
                             code0 = kCodeAgent + (int)((ap0 >> 8) & 15u);
-                            code1 = code0 + 16;
                         } else if ((ap1 & 0xffu) == xy) {
-                            code1 = kCodeAgent + (int)((ap1 >> 8) & 15u);
-                            code0 = code1 + 16;
+                            code0 = kCodeAgent + 16 + (int)((ap1 >> 8) & 15u);
                         } else {
                             const int o = c[0];
                             code0 = (o == 8) ? kCodePot + min((int)c[2], 23) : min(o, 10);
-                            code1 = code0;
                         }
                     }
                     const uint4 *r0 = reinterpret_cast<const uint4 *>(s_rec + code0 * kRecWords + 8 * u);
-                    const uint4 *r1 = reinterpret_cast<const uint4 *>(s_rec + code1 * kRecWords + 8 * u);
-                    uint4 v0 = r0[0], v1 = r0[1], w0 = r1[0], w1 = r1[1];
-                    const uint32_t ub = urgbit << (u ? 24 : 8);                 // channel 25 (:311, :341)
-                    v1.z |= ub; w1.z |= ub;
-                    uint32_t *d0 = u ? rB0 : rA0, *d1 = u ? rB1 : rA1;
+                    uint4 v0 = r0[0], v1 = r0[1];
+                    v1.z |= urgbit << (u ? 24 : 8);                             // channel 25 (:311, :341)
+                    uint32_t *d0 = u ? rB : rA;
                     d0[0] = v0.x; d0[1] = v0.y; d0[2] = v0.z; d0[3] = v0.w; d0[4] = v1.x; d0[5] = v1.y; d0[6] = v1.z; d0[7] = v1.w;
-                    d1[0] = w0.x; d1[1] = w0.y; d1[2] = w0.z; d1[3] = w0.w; d1[4] = w1.x; d1[5] = w1.y; d1[6] = w1.z; d1[7] = w1.w;
                 }
-                uint32_t *o0 = stage0 + q * 13, *o1 = stage1 + q * 13;
+                uint32_t *o0 = stage0 + q * 13;
                 #pragma unroll
-                for (int k = 0; k < 6; ++k) { o0[k] = rA0[k]; o1[k] = rA1[k]; }
-                o0[6] = rA0[6] | rB0[0]; o1[6] = rA1[6] | rB1[0];
+                for (int k = 0; k < 6; ++k) o0[k] = rA[k];
+                o0[6] = rA[6] | rB[0];
                 #pragma unroll
-                for (int k = 1; k < 7; ++k) { o0[6 + k] = rB0[k]; o1[6 + k] = rB1[k]; }
+                for (int k = 1; k < 7; ++k) o0[6 + k] = rB[k];
             }
             const size_t obs_off = (size_t)env0 * C * OC_OBS_CHANNELS;
+            // this lane's agent cell as agent_1 sees it: "which" flipped (agent_1 is the viewer)
+            patch_valid = active;
+            patch_off = ((size_t)env * C + (size_t)(ny * w + nx)) * OC_OBS_CHANNELS;
+            patch_code = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
             if (p.bulk_ok && n_valid == epw) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -485,19 +527,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage0)), "r"(view_bytes) : "memory");
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage1)), "r"(view_bytes) : "memory");
+                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage0)), "r"(view_bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 bulk_pending = true;
             } else {
-                // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular
+                // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular, patch right away
                 __syncwarp();
                 const int nb = n_cells * OC_OBS_CHANNELS;   // even
                 const unsigned short *h0 = reinterpret_cast<const unsigned short *>(stage0);
-                const unsigned short *h1 = reinterpret_cast<const unsigned short *>(stage1);
                 unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + obs_off);
                 unsigned short *g1 = reinterpret_cast<unsigned short *>(p.obs1 + obs_off);
-                for (int k = lane; k < (nb >> 1); k += 32) { g0[k] = h0[k]; g1[k] = h1[k]; }
+                for (int k = lane; k < (nb >> 1); k += 32) { const unsigned short v = h0[k]; g0[k] = v; g1[k] = v; }
+                __syncwarp();
+                apply_patch();
             }
         }
 
@@ -573,7 +616,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         }
         __syncwarp();
     }
-    if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (bulk_pending) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        apply_patch();
+    }
 }
 
 // oc_reset pre-pass: constant ring + static State fields (the reset kernel then fills interior and dynamics)
@@ -632,7 +679,8 @@ struct oc_layout {
     int epw;
     int smem_bytes;
     int warp_bytes;
-    int max_ctas;      // persistent-grid cap: SM count x resident CTAs per SM
+    int num_sms;
+    mutable int occ[3];   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
 
 namespace {
@@ -691,7 +739,6 @@ bool state_aligned(const oc_state &s) {
 
 template <int MODE>
 int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
-    static bool attr_set[16][3] = {};
     const DevLayout &H = lay->host;
     kp.L = lay->dev;
     kp.epw = lay->epw;
@@ -702,16 +749,22 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
-    long long ctas = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (ctas > lay->max_ctas) ctas = lay->max_ctas;
-    if (ctas < 1) return OC_OK;
-    if (lay->device < 16 && !attr_set[lay->device][MODE]) {
+    if (kp.n_tiles < 1) return OC_OK;
+    if (lay->occ[MODE] == 0) {
         if (cudaFuncSetAttribute(oc_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
-        attr_set[lay->device][MODE] = true;
-    } else if (lay->device >= 16) {
-        if (cudaFuncSetAttribute(oc_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oc_env_kernel<MODE>, kWarpsPerCta * 32, lay->smem_bytes) != cudaSuccess)
             return fail_cuda();
+        lay->occ[MODE] = nb < 1 ? 1 : nb;
+    }
+    // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
+    const long long resident = (long long)lay->num_sms * lay->occ[MODE];
+    const long long want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    long long ctas = want;
+    if (want > resident) {
+        const long long k = (want + resident - 1) / resident;
+        ctas = (want + k - 1) / k;
     }
     oc_env_kernel<MODE><<<(unsigned)ctas, kWarpsPerCta * 32, lay->smem_bytes, stream>>>(kp);
     return cudaGetLastError() == cudaSuccess ? OC_OK : fail_cuda();
@@ -836,7 +889,7 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // tile shape: the largest envs-per-warp that still leaves >= 4 CTAs (16 warps) resident per SM, subject to the
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
-    auto warp_bytes_for = [&](int e) { return ((2 * e * C * OC_OBS_CHANNELS + e * L.span_stride + 2 * e * 4) + 15) & ~15; };
+    auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     int epw = 0;
     for (int e = 16; e >= 2; e >>= 1)
@@ -853,10 +906,8 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->epw = epw;
     lay->warp_bytes = warp_bytes_for(epw);
     lay->smem_bytes = kHdrBytesHost + kWarpsPerCta * lay->warp_bytes;
-    int per_sm = smem_cap / (lay->smem_bytes + 1024);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16) per_sm = 16;
-    lay->max_ctas = prop.multiProcessorCount * per_sm * 8;   // a few waves; the kernel grid-strides beyond that
+    lay->num_sms = prop.multiProcessorCount;
+    lay->occ[0] = lay->occ[1] = lay->occ[2] = 0;
     lay->device = device;
     if (cudaMalloc(&lay->dev, sizeof(DevLayout)) != cudaSuccess) { delete lay; return fail_cuda(); }
     if (cudaMemcpy(lay->dev, &L, sizeof(DevLayout), cudaMemcpyHostToDevice) != cudaSuccess) {
