@@ -43,6 +43,8 @@ constexpr int kCodeAgent = 35;
 constexpr int kMaxSpanBytes = ((OC_MAX_DIM - 1) * (OC_MAX_DIM + 2 * OC_PAD) + OC_MAX_DIM) * 3;   // 1128
 constexpr int kMaxMapBytes = (OC_MAX_DIM + 2 * OC_PAD) * (OC_MAX_DIM + 2 * OC_PAD) * 3;          // 1728
 constexpr int kWarpsPerCta = 4;
+constexpr int kMaxTmplBytes = 8 * OC_MAX_CELLS * OC_OBS_CHANNELS;        // worst case: odd cell count -> 8 copies
+constexpr int kHdrFixed = kNumCodes * kRecWords * 4 + 64 + 32 + OC_MAX_CELLS * 4;   // rec, bitmaps, pots, scan list
 
 struct DevLayout {
     int h, w, C, WP;
@@ -54,9 +56,12 @@ struct DevLayout {
     unsigned wall_bits[8], blocked_bits[8];   // wall_map; wall_map | goal cells (movement blocking)
     unsigned short pot_cell[OC_MAX_SPECIAL];
     unsigned short goal_cell[OC_MAX_SPECIAL];
-    unsigned rec[kNumCodes][kRecWords];
+    alignas(16) unsigned rec[kNumCodes][kRecWords];
     unsigned char tmpl_span[kMaxSpanBytes + 8];   // interior span right after a reset, without agents, pots = 23
     unsigned char tmpl_full[kMaxMapBytes];        // whole padded map, same contents (oc_reset initialisation)
+    int n_scan, tmpl_k, tmpl_chunks;
+    unsigned scan[OC_MAX_CELLS];                  // cells that can deviate from the base image: span offset | cell << 16
+    alignas(16) unsigned char obs_tmpl[kMaxTmplBytes];        // tmpl_k back-to-back copies of the layout's static observation
 };
 
 struct KParams {
@@ -79,6 +84,8 @@ struct KParams {
     int h, w, C, WP, map_bytes, span_off, span_len, span_words, span_stride, n_pot, max_steps, random_reset, part;
     int agent_cell0, agent_cell1;
     unsigned magic_C, magic_w, magic_sw;
+    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes;
+    unsigned magic_ns, magic_tc;
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBS = 2 };
@@ -199,27 +206,33 @@ template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
+    // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
     uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem);
     uint32_t *s_bits = s_rec + kNumCodes * kRecWords;                    // [0..7] wall, [8..15] blocked
     unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
-    constexpr int kHdrBytes = kNumCodes * kRecWords * 4 + 64 + 32;
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_pot + OC_MAX_SPECIAL);   // [n_scan] span offset | cell << 16
+    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed);          // [tmpl_chunks] k envs of the base image
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // CTA-wide constants -> shared memory
+    {
         const uint4 *src = reinterpret_cast<const uint4 *>(&L->rec[0][0]);
         uint4 *dst = reinterpret_cast<uint4 *>(s_rec);
         for (int i = tid; i < kNumCodes * kRecWords / 4; i += kWarpsPerCta * 32) dst[i] = __ldg(src + i);
+        const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
+        for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
+        for (int i = tid; i < p.n_scan; i += kWarpsPerCta * 32) s_scan[i] = L->scan[i];
         if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
         if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
     }
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
     const int epw = p.epw;
-    const int span_stride = p.span_stride, span_words = p.span_words;
+    const int span_stride = p.span_stride, span_words = p.span_words, sstride_w = p.span_stride >> 2;
     const int part = p.part;
-    const int view_bytes = epw * C * OC_OBS_CHANNELS;
-    unsigned char *wbase = smem + kHdrBytes + (size_t)warp * p.warp_bytes;
-    uint32_t *stage0 = reinterpret_cast<uint32_t *>(wbase);                    // agent_0's view of the tile
-    unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride], double-buffered
+    const int env_bytes = C * OC_OBS_CHANNELS;
+    const int view_bytes = epw * env_bytes;
+    unsigned char *wbase = smem + kHdrFixed + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
+    unsigned char *stage = wbase;                                              // agent_0's view of the tile
+    unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
     uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] packed agent state
     __syncthreads();
 
@@ -242,22 +255,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         }
         patch_valid = false;
     };
+    // write one cell's 26-byte record into the staged image at flat cell index g (2-byte aligned offset g*26)
+    auto stage_record = [&](int g, int code) {
+        const uint32_t *r = s_rec + code * kRecWords + ((g & 1) ? 8 : 0);
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(r), v1 = *reinterpret_cast<const uint4 *>(r + 4);
+        unsigned char *dst = stage + g * OC_OBS_CHANNELS;
+        if (g & 1) {   // offset = 2 (mod 4): shifted record -- upper half of word 0, then words 1..6
+            *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(v0.x >> 16);
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst + 2);
+            d[0] = v0.y; d[1] = v0.z; d[2] = v0.w; d[3] = v1.x; d[4] = v1.y; d[5] = v1.z;
+        } else {       // word aligned: words 0..5, then the lower half of word 6
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+            d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y;
+            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)(v1.z & 0xffffu);
+        }
+    };
 
-    // cp.async (LDGSTS) of one tile's interior spans into span buffer `b`: 4-byte granular because an env's
-    // maze_map is only guaranteed 1-byte... tile-relative word alignment (map_bytes need not be a multiple of 4)
+    // cp.async (LDGSTS) of one tile's interior spans into span buffer `b`; word-granular because an env's
+    // maze_map is only byte-aligned relative to its neighbours (map_bytes need not be a multiple of 4)
     const long long tile_stride = (long long)gridDim.x * kWarpsPerCta;
     auto prefetch_spans = [&](long long tl, int b) {
         const long long e0 = tl * epw;
         const int nv = (int)min((long long)epw, p.N - e0);
-        const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map);
-        uint32_t *dstw = reinterpret_cast<uint32_t *>(smap_buf + b * epw * span_stride);
+        const long long base = e0 * (long long)p.map_bytes + p.span_off;   // byte offset of env e0's span
+        const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map) + (base >> 2);
+        const int r0 = (int)(base & 3);
+        const uint32_t dst0 = smem_u32(smap_buf + b * epw * span_stride);
         const int total = nv * span_words;
+        int el = (int)fastdiv((unsigned)lane, p.magic_sw), k = lane - el * span_words;
         for (int f = lane; f < total; f += 32) {
-            const int el = (int)fastdiv((unsigned)f, p.magic_sw);
-            const int k = f - el * span_words;
-            const long long gb = (e0 + el) * (long long)p.map_bytes + p.span_off;
+            const int wi = ((r0 + el * p.map_bytes) >> 2) + k;              // word index relative to mw
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                         :: "r"(smem_u32(dstw + el * (span_stride >> 2) + k)), "l"(mw + (gb >> 2) + k) : "memory");
+                         :: "r"(dst0 + 4u * (unsigned)(el * sstride_w + k)), "l"(mw + wi) : "memory");
+            k += 32;
+            while (k >= span_words) { k -= span_words; ++el; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -291,12 +322,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         const bool active = e < n_valid;
         const int es = active ? e : 0;            // idle lanes shadow env 0 of the tile (reads only)
         const long long env = env0 + es;
-        // byte offset (within maze_map) of this env's interior span, and its word misalignment
-        const long long gb_lane = env * (long long)p.map_bytes + p.span_off;
-        const int shift_lane = (int)(gb_lane & 3);
+        // byte offset (within maze_map) of the tile's first interior span; per-env word misalignment
+        const long long base0 = env0 * (long long)p.map_bytes + p.span_off;
+        const int r0 = (int)(base0 & 3);
         unsigned char *smap = smap_buf + buf * epw * span_stride;
         uint32_t *smap_w = reinterpret_cast<uint32_t *>(smap);
-        unsigned char *my_span = smap + es * span_stride + shift_lane;
+        unsigned char *my_span = smap + es * span_stride + ((r0 + es * p.map_bytes) & 3);
+        unsigned char *g_span = p.st.maze_map + env * (long long)p.map_bytes + p.span_off;   // same bytes in HBM
 
         // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
         const Fields cf = nf;
@@ -314,6 +346,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         int nx = px, ny = py, ndi = di, ninv = inv, t_out = t, term_out = 0;
         bool done = (MODE == MODE_RESET);
         int rew = 0, shaped = 0;
+        // a cell is updated in the staged span AND, in place, in HBM (only cells that change are ever written back)
+        auto put_cell = [&](int off, int a, int b, int c) {
+            my_span[off] = (unsigned char)a; my_span[off + 1] = (unsigned char)b; my_span[off + 2] = (unsigned char)c;
+            g_span[off] = (unsigned char)a; g_span[off + 1] = (unsigned char)b; g_span[off + 2] = (unsigned char)c;
+        };
 
         if (MODE == MODE_STEP) {
             // ------------------------------------------------------------ movement (overcooked.py:370-431)
@@ -335,34 +372,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
             // ------------------------------------------------------------ interact (:437-468, :516-642)
             const int fx = clampi(px + dx, 0, w - 1), fy = clampi(py + dy, 0, h - 1);   // old pos + old dir
             const int fc = fy * w + fx;
-            unsigned char *cp = my_span + (fy * WP + fx) * 3;
+            const int foff = (fy * WP + fx) * 3;
             const bool wallbit = (s_bits[fc >> 5] >> (fc & 31)) & 1u;
             const bool do_int = active & (act == 5);
-            Interact r = interact_cell(cp[0], cp[2], inv, wallbit);
-            if (do_int && ai == 0 && r.write) { cp[0] = (unsigned char)r.obj; cp[1] = (unsigned char)obj_colour(r.obj); cp[2] = (unsigned char)r.status; }
+            Interact r = interact_cell(my_span[foff], my_span[foff + 2], inv, wallbit);
+            if (do_int && ai == 0 && r.write) put_cell(foff, r.obj, obj_colour(r.obj), r.status);
             __syncwarp();
             const int a_fc = __shfl_sync(0xffffffffu, fc, lane & ~1);
             const int a_did = __shfl_sync(0xffffffffu, (int)do_int, lane & ~1);
             if (do_int && ai == 1) {
-                if (a_did && a_fc == fc) r = interact_cell(cp[0], cp[2], inv, wallbit);   // Bob sees Alice's update
-                if (r.write) { cp[0] = (unsigned char)r.obj; cp[1] = (unsigned char)obj_colour(r.obj); cp[2] = (unsigned char)r.status; }
+                if (a_did && a_fc == fc) r = interact_cell(my_span[foff], my_span[foff + 2], inv, wallbit);   // Bob sees Alice's update
+                if (r.write) put_cell(foff, r.obj, obj_colour(r.obj), r.status);
             }
             __syncwarp();
             if (do_int) { ninv = r.inv; rew = r.delivery ? 20 : 0; shaped = r.shaped; }
 
             // ------------------------------------------------------------ redraw agents (:470-486)
-            if (active) { unsigned char *c0 = my_span + (py * WP + px) * 3; c0[0] = 1; c0[1] = 0; c0[2] = 0; }
+            if (active) put_cell((py * WP + px) * 3, 1, 0, 0);
             __syncwarp();
-            if (active) { unsigned char *c1 = my_span + (ny * WP + nx) * 3; c1[0] = 10; c1[1] = (unsigned char)(2 * ai); c1[2] = (unsigned char)ndi; }
+            if (active) put_cell((ny * WP + nx) * 3, 10, 2 * ai, ndi);
             __syncwarp();
             // ------------------------------------------------------------ pot timers (:488-500)
             if (active) {
                 for (int q = ai; q < p.n_pot; q += 2) {
                     const int pc = s_pot[q];
                     const int pyy = (int)fastdiv((unsigned)pc, p.magic_w), pxx = pc - pyy * w;
-                    unsigned char *c = my_span + (pyy * WP + pxx) * 3;
-                    const int s = c[2];
-                    if (s >= 1 && s <= 20) c[2] = (unsigned char)(s - 1);
+                    const int off = (pyy * WP + pxx) * 3 + 2;
+                    const int s = my_span[off];
+                    if (s >= 1 && s <= 20) { my_span[off] = (unsigned char)(s - 1); g_span[off] = (unsigned char)(s - 1); }
                 }
             }
             rew += __shfl_xor_sync(0xffffffffu, rew, 1);                   // :502 reward = alice + bob
@@ -372,16 +409,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         }
 
         // -------------------------------------------------------------------- (3) reset (overcooked.py:136-248)
+        bool full_writeback = (MODE == MODE_RESET);
         if (MODE != MODE_OBS) {
             const unsigned done_mask = __ballot_sync(0xffffffffu, done && active);
             if (done_mask) {
+                full_writeback = true;
                 if (MODE == MODE_STEP && p.has_rs) {
                     // multi_agent_env.py:55-59: caller-supplied reset_state replaces reset(key_reset)
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.rs.maze_map);
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.rs.maze_map) + (base0 >> 2);
                     for (int el = 0; el < n_valid; ++el) {
                         if (!((done_mask >> (2 * el)) & 1u)) continue;
-                        const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
-                        for (int k = lane; k < span_words; k += 32) smap_w[el * (span_stride >> 2) + k] = __ldg(rw + (gb >> 2) + k);
+                        const int wo = (r0 + el * p.map_bytes) >> 2;
+                        for (int k = lane; k < span_words; k += 32) smap_w[el * sstride_w + k] = __ldg(rw + wo + k);
                     }
                     if (done && active) {
                         const uint2 pp = __ldg(reinterpret_cast<const uint2 *>(p.rs.agent_pos) + env * 2 + ai);
@@ -396,8 +435,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
                     // template interior for every finished env (warp-cooperative byte copy)
                     for (int el = 0; el < n_valid; ++el) {
                         if (!((done_mask >> (2 * el)) & 1u)) continue;
-                        const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
-                        unsigned char *dst = smap + el * span_stride + (int)(gb & 3);
+                        unsigned char *dst = smap + el * span_stride + ((r0 + el * p.map_bytes) & 3);
                         for (int k = lane; k < p.span_len; k += 32) dst[k] = __ldg(L->tmpl_span + k);
                     }
                     __syncwarp();
@@ -465,57 +503,56 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
         {
             const int urg = (p.max_steps - t_out) < 40;                                       // :311
-            if (active)
-                s_ap[lane] = (uint32_t)nx | ((uint32_t)ny << 4) | ((uint32_t)ndi << 8) | ((uint32_t)inv_code(ninv) << 10) |
-                             ((uint32_t)urg << 12);
+            if (active) s_ap[lane] = (uint32_t)urg;
             if (bulk_pending) {   // the previous tile's bulk copies must be COMPLETE: staging is reused, obs1 is patched
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 bulk_pending = false;
                 __syncwarp();
                 apply_patch();
             }
-            __syncwarp();
-            const int n_cells = n_valid * C;
-            const int n_pairs = (n_cells + 1) >> 1;
-            for (int q = lane; q < n_pairs; q += 32) {
-                uint32_t rA[8], rB[8];
-                #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int g = 2 * q + u;
-                    int code0 = 0;
-                    uint32_t urgbit = 0;
-                    if (g < n_cells) {
-                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
-                        const int cell = g - el * C;
-                        const int y = (int)fastdiv((unsigned)cell, p.magic_w), x = cell - y * w;
-                        const uint32_t ap0 = s_ap[2 * el], ap1 = s_ap[2 * el + 1];
-                        const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
-                        const unsigned char *c = smap + el * span_stride + (int)(gb & 3) + (y * WP + x) * 3;
-                        const uint32_t xy = (uint32_t)x | ((uint32_t)y << 4);
-                        urgbit = (ap0 >> 12) & 1u;
-                        if ((ap0 & 0xffu) == xy) {            // :313-319 agent cells show the inventory
-                            code0 = kCodeAgent + (int)((ap0 >> 8) & 15u);
-                        } else if ((ap1 & 0xffu) == xy) {
-                            code0 = kCodeAgent + 16 + (int)((ap1 >> 8) & 15u);
-                        } else {
-                            const int o = c[0];
-                            code0 = (o == 8) ? kCodePot + min((int)c[2], 23) : min(o, 10);
-                        }
-                    }
-                    const uint4 *r0 = reinterpret_cast<const uint4 *>(s_rec + code0 * kRecWords + 8 * u);
-                    uint4 v0 = r0[0], v1 = r0[1];
-                    v1.z |= urgbit << (u ? 24 : 8);                             // channel 25 (:311, :341)
-                    uint32_t *d0 = u ? rB : rA;
-                    d0[0] = v0.x; d0[1] = v0.y; d0[2] = v0.z; d0[3] = v0.w; d0[4] = v1.x; d0[5] = v1.y; d0[6] = v1.z; d0[7] = v1.w;
+            // (4a) base image: the layout's static observation (no agents, empty pots), 16 bytes per lane-step
+            {
+                const int n_chunks = (n_valid * env_bytes + 15) >> 4;
+                const int phase = (int)(((env0 % p.tmpl_k) * (long long)env_bytes) >> 4);
+                uint4 *dst = reinterpret_cast<uint4 *>(stage);
+                int src = phase + lane;
+                src -= (int)fastdiv((unsigned)src, p.magic_tc) * p.tmpl_chunks;
+                const int step = 32 - (int)fastdiv(32u, p.magic_tc) * p.tmpl_chunks;      // 32 mod tmpl_chunks
+                for (int f = lane; f < n_chunks; f += 32) {
+                    dst[f] = s_tmpl[src];
+                    src += step;
+                    if (src >= p.tmpl_chunks) src -= p.tmpl_chunks;
                 }
-                uint32_t *o0 = stage0 + q * 13;
-                #pragma unroll
-                for (int k = 0; k < 6; ++k) o0[k] = rA[k];
-                o0[6] = rA[6] | rB[0];
-                #pragma unroll
-                for (int k = 1; k < 7; ++k) o0[6 + k] = rB[k];
             }
-            const size_t obs_off = (size_t)env0 * C * OC_OBS_CHANNELS;
+            __syncwarp();
+            // (4b) cells that can deviate from the base image: counters next to a walkable cell (loose items) and pots
+            {
+                const int total = n_valid * p.n_scan;
+                for (int f = lane; f < total; f += 32) {
+                    const int el = (int)fastdiv((unsigned)f, p.magic_ns);
+                    const uint32_t sc = s_scan[f - el * p.n_scan];
+                    const unsigned char *c = smap + el * span_stride + ((r0 + el * p.map_bytes) & 3) + (int)(sc & 0xffffu);
+                    const int o = c[0], st = c[2];
+                    if (o == 8 ? (st != 23) : (o != 2 && o != 10))
+                        stage_record(el * C + (int)(sc >> 16), (o == 8) ? kCodePot + min(st, 23) : min(o, 10));
+                }
+            }
+            __syncwarp();
+            // (4c) agent cells show the agent, its direction and what it holds (:313-323, :345-353)
+            if (active) stage_record(es * C + ny * w + nx, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)));
+            __syncwarp();
+            // (4d) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left
+            {
+                const unsigned urg_mask = __ballot_sync(0xffffffffu, active && urg && ai == 0);
+                if (urg_mask) {
+                    const int n_cells = n_valid * C;
+                    for (int g = lane; g < n_cells; g += 32) {
+                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
+                        if (s_ap[2 * el]) stage[g * OC_OBS_CHANNELS + 25] = 1;
+                    }
+                }
+            }
+            const size_t obs_off = (size_t)env0 * env_bytes;
             // this lane's agent cell as agent_1 sees it: "which" flipped (agent_1 is the viewer)
             patch_valid = active;
             patch_off = ((size_t)env * C + (size_t)(ny * w + nx)) * OC_OBS_CHANNELS;
@@ -525,17 +562,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
                 __syncwarp();
                 if (lane == 0) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage0)), "r"(view_bytes) : "memory");
+                                 :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage0)), "r"(view_bytes) : "memory");
+                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 bulk_pending = true;
             } else {
                 // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular, patch right away
                 __syncwarp();
-                const int nb = n_cells * OC_OBS_CHANNELS;   // even
-                const unsigned short *h0 = reinterpret_cast<const unsigned short *>(stage0);
+                const int nb = n_valid * env_bytes;   // even
+                const unsigned short *h0 = reinterpret_cast<const unsigned short *>(stage);
                 unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + obs_off);
                 unsigned short *g1 = reinterpret_cast<unsigned short *>(p.obs1 + obs_off);
                 for (int k = lane; k < (nb >> 1); k += 32) { const unsigned short v = h0[k]; g0[k] = v; g1[k] = v; }
@@ -547,13 +584,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         // ---------------------------------------------------------------- (5) write the state back, in place
         if (MODE != MODE_OBS) {
             __syncwarp();
-            uint32_t *mw = reinterpret_cast<uint32_t *>(p.st.maze_map);
-            const int total = n_valid * span_words;
-            for (int f = lane; f < total; f += 32) {
-                const int el = (int)fastdiv((unsigned)f, p.magic_sw);
-                const int k = f - el * span_words;
-                const long long gb = (env0 + el) * (long long)p.map_bytes + p.span_off;
-                mw[(gb >> 2) + k] = smap_w[el * (span_stride >> 2) + k];
+            if (full_writeback) {   // a reset rewrote whole interiors: store the staged spans (rare: 1 step in max_steps)
+                uint32_t *mw = reinterpret_cast<uint32_t *>(p.st.maze_map) + (base0 >> 2);
+                const int total = n_valid * span_words;
+                int el = (int)fastdiv((unsigned)lane, p.magic_sw), k = lane - el * span_words;
+                for (int f = lane; f < total; f += 32) {
+                    mw[((r0 + el * p.map_bytes) >> 2) + k] = smap_w[el * sstride_w + k];
+                    k += 32;
+                    while (k >= span_words) { k -= span_words; ++el; }
+                }
             }
             if (active) {
                 reinterpret_cast<uint2 *>(p.st.agent_pos)[env * 2 + ai] = make_uint2((uint32_t)nx, (uint32_t)ny);
@@ -623,6 +662,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
     }
 }
 
+
 // oc_reset pre-pass: constant ring + static State fields (the reset kernel then fills interior and dynamics)
 __global__ void oc_init_static_kernel(const DevLayout *__restrict__ L, long long N, oc_state st) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -685,7 +725,6 @@ struct oc_layout {
 
 namespace {
 
-constexpr int kHdrBytesHost = kNumCodes * kRecWords * 4 + 64 + 32;
 
 unsigned magic_of(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
 
@@ -748,6 +787,8 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
+    kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = H.tmpl_chunks * 16;
+    kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
     if (lay->occ[MODE] == 0) {
@@ -884,11 +925,40 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
         for (int i = 0; i < d->n_plate_pile; ++i) put(d->plate_pile_idx[i], 6, 6, 0);
         for (int i = 0; i < d->n_pot; ++i) put(d->pot_idx[i], 8, 7, 23);
         std::memcpy(L.tmpl_span, m + L.span_off, (size_t)L.span_len);
+        // cells whose observation can deviate from the static image without being an agent cell: pots, and plain
+        // counters an agent can face (4-neighbours of a walkable cell) -- the only cells interact ever rewrites
+        L.n_scan = 0;
+        for (int c = 0; c < C; ++c) {
+            const int y = c / w, x = c % w;
+            const unsigned char *q = m + ((OC_PAD + y) * WP + OC_PAD + x) * 3;
+            bool near_free = false;
+            if (y > 0 && !wall[c - w]) near_free = true;
+            if (y < h - 1 && !wall[c + w]) near_free = true;
+            if (x > 0 && !wall[c - 1]) near_free = true;
+            if (x < w - 1 && !wall[c + 1]) near_free = true;
+            if (q[0] == 8 || (q[0] == 2 && wall[c] && near_free))
+                L.scan[L.n_scan++] = (unsigned)((y * WP + x) * 3) | ((unsigned)c << 16);
+        }
+        // static observation of one env (agent_0's view == agent_1's view without agents), repeated tmpl_k times so
+        // that the copy period is a whole number of 16-byte chunks
+        const int env_bytes = C * OC_OBS_CHANNELS;
+        int g = env_bytes, b16 = 16;
+        while (b16) { const int t = g % b16; g = b16; b16 = t; }
+        L.tmpl_k = 16 / g;
+        L.tmpl_chunks = L.tmpl_k * env_bytes / 16;
+        for (int k = 0; k < L.tmpl_k; ++k)
+            for (int c = 0; c < C; ++c) {
+                const unsigned char *q = m + ((OC_PAD + c / w) * WP + OC_PAD + c % w) * 3;
+                unsigned char v[32];
+                fill_record(q[0] == 8 ? kCodePot + 23 : q[0], v);
+                std::memcpy(L.obs_tmpl + (size_t)k * env_bytes + (size_t)c * OC_OBS_CHANNELS, v, OC_OBS_CHANNELS);
+            }
     }
 
     // tile shape: the largest envs-per-warp that still leaves >= 4 CTAs (16 warps) resident per SM, subject to the
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
+    const int kHdrBytesHost = kHdrFixed + L.tmpl_chunks * 16;
     auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     int epw = 0;
