@@ -44,7 +44,7 @@ constexpr int kMaxSpanBytes = ((OC_MAX_DIM - 1) * (OC_MAX_DIM + 2 * OC_PAD) + OC
 constexpr int kMaxMapBytes = (OC_MAX_DIM + 2 * OC_PAD) * (OC_MAX_DIM + 2 * OC_PAD) * 3;          // 1728
 constexpr int kWarpsPerCta = 4;
 constexpr int kMaxTmplBytes = 8 * OC_MAX_CELLS * OC_OBS_CHANNELS;        // worst case: odd cell count -> 8 copies
-constexpr int kHdrFixed = kNumCodes * kRecWords * 4 + 64 + 32 + OC_MAX_CELLS * 4;   // rec, bitmaps, pots, scan list
+constexpr int kHdrFixed = 64 + 32;   // wall/blocked bitmaps, pot cells; then the scan list and the observation template
 
 struct DevLayout {
     int h, w, C, WP;
@@ -84,7 +84,7 @@ struct KParams {
     int h, w, C, WP, map_bytes, span_off, span_len, span_words, span_stride, n_pot, max_steps, random_reset, part;
     int agent_cell0, agent_cell1;
     unsigned magic_C, magic_w, magic_sw;
-    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes;
+    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes;
     unsigned magic_ns, magic_tc;
 };
 
@@ -203,62 +203,39 @@ __device__ __forceinline__ Interact interact_cell(int obj, int status, int inv, 
 // ------------------------------------------------------------------------------------------------ kernel
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
     // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
-    uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *s_bits = s_rec + kNumCodes * kRecWords;                    // [0..7] wall, [8..15] blocked
+    // (the 68-entry record table stays in global memory: it is only touched for the few cells per env that deviate
+    //  from the static image, and 4.3 KB of it live in L1)
+    const uint32_t *__restrict__ g_rec = &L->rec[0][0];
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem);                // [0..7] wall, [8..15] blocked
     unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
-    uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_pot + OC_MAX_SPECIAL);   // [n_scan] span offset | cell << 16
-    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed);          // [tmpl_chunks] k envs of the base image
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + kHdrFixed);   // [n_scan] span offset | cell << 16
+    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed + p.scan_bytes);   // [tmpl_chunks] k envs of the base image
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&L->rec[0][0]);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_rec);
-        for (int i = tid; i < kNumCodes * kRecWords / 4; i += kWarpsPerCta * 32) dst[i] = __ldg(src + i);
-        const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
-        for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
-        for (int i = tid; i < p.n_scan; i += kWarpsPerCta * 32) s_scan[i] = L->scan[i];
-        if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
-        if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
-    }
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
     const int epw = p.epw;
     const int span_stride = p.span_stride, span_words = p.span_words, sstride_w = p.span_stride >> 2;
     const int part = p.part;
     const int env_bytes = C * OC_OBS_CHANNELS;
     const int view_bytes = epw * env_bytes;
-    unsigned char *wbase = smem + kHdrFixed + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
+    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
     unsigned char *stage = wbase;                                              // agent_0's view of the tile
     unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
     uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] packed agent state
-    __syncthreads();
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
     bool bulk_pending = false;
-    // agent_1's view differs from agent_0's only in bytes 0..9 of the two agent cells (overcooked.py:356-359):
-    // both observation buffers receive the SAME staged image through the bulk-copy engine, and each lane then
-    // rewrites its own agent cell's 10 bytes in obs1 once that copy has completed (deferred to the next tile).
-    bool patch_valid = false;
-    size_t patch_off = 0;
-    int patch_code = 0;
-    auto apply_patch = [&]() {
-        if (patch_valid) {
-            const uint32_t *r = s_rec + patch_code * kRecWords;
-            const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
-            unsigned short *g = reinterpret_cast<unsigned short *>(p.obs1 + patch_off);
-            g[0] = (unsigned short)(w0 & 0xffffu); g[1] = (unsigned short)(w0 >> 16);
-            g[2] = (unsigned short)(w1 & 0xffffu); g[3] = (unsigned short)(w1 >> 16);
-            g[4] = (unsigned short)(w2 & 0xffffu);
-        }
-        patch_valid = false;
-    };
+    // agent_1's view differs from agent_0's only in the two agent cells (overcooked.py:356-359): the staged image is
+    // sent to obs0, then -- as soon as the copy engine has READ it -- the two agent cells are re-staged from
+    // agent_1's perspective and the same buffer is sent to obs1.
     // write one cell's 26-byte record into the staged image at flat cell index g (2-byte aligned offset g*26)
     auto stage_record = [&](int g, int code) {
-        const uint32_t *r = s_rec + code * kRecWords + ((g & 1) ? 8 : 0);
-        const uint4 v0 = *reinterpret_cast<const uint4 *>(r), v1 = *reinterpret_cast<const uint4 *>(r + 4);
+        const uint32_t *r = g_rec + code * kRecWords + ((g & 1) ? 8 : 0);
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(r)), v1 = __ldg(reinterpret_cast<const uint4 *>(r + 4));
         unsigned char *dst = stage + g * OC_OBS_CHANNELS;
         if (g & 1) {   // offset = 2 (mod 4): shifted record -- upper half of word 0, then words 1..6
             *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(v0.x >> 16);
@@ -283,19 +260,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         const uint32_t dst0 = smem_u32(smap_buf + b * epw * span_stride);
         const int total = nv * span_words;
         int el = (int)fastdiv((unsigned)lane, p.magic_sw), k = lane - el * span_words;
+        int gw = ((r0 + el * p.map_bytes) >> 2) + k;                        // word index relative to mw
+        unsigned so = dst0 + 4u * (unsigned)(el * sstride_w + k);
         for (int f = lane; f < total; f += 32) {
-            const int wi = ((r0 + el * p.map_bytes) >> 2) + k;              // word index relative to mw
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                         :: "r"(dst0 + 4u * (unsigned)(el * sstride_w + k)), "l"(mw + wi) : "memory");
-            k += 32;
-            while (k >= span_words) { k -= span_words; ++el; }
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(so), "l"(mw + gw) : "memory");
+            k += 32; gw += 32; so += 128u;
+            while (k >= span_words) {
+                k -= span_words; ++el;
+                gw = ((r0 + el * p.map_bytes) >> 2) + k;
+                so = dst0 + 4u * (unsigned)(el * sstride_w + k);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    struct Fields { uint2 pos; char2 dir; int di, inv, t, act; };
+    struct Fields { uint2 pos; unsigned short dir; int di, inv, t, act; };   // raw, unpacked only when consumed
     auto load_fields = [&](long long tl) {
         Fields f;
-        f.pos = make_uint2(0u, 0u); f.dir = make_char2(0, 0); f.di = 0; f.inv = 1; f.t = 0; f.act = 4;
+        f.pos = make_uint2(0u, 0u); f.dir = 0; f.di = 0; f.inv = 1; f.t = 0; f.act = 4;
         const long long e0 = tl * epw;
         const int nv = (int)min((long long)epw, p.N - e0);
         if (e < nv && MODE != MODE_RESET) {
@@ -305,7 +286,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
             f.inv = p.st.agent_inv[en * 2 + ai];
             f.t = p.st.time[en];
             if (MODE == MODE_STEP) {
-                f.dir = reinterpret_cast<const char2 *>(p.st.agent_dir)[en * 2 + ai];
+                f.dir = reinterpret_cast<const unsigned short *>(p.st.agent_dir)[en * 2 + ai];
                 f.act = __ldg((ai ? p.act1 : p.act0) + en);
             }
         }
@@ -315,6 +296,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
     int buf = 0;
     Fields nf;
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
+    // CTA-shared tables are fetched while the first tile's state is already in flight
+    {
+        const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
+        for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
+        for (int i = tid; i < p.n_scan; i += kWarpsPerCta * 32) s_scan[i] = L->scan[i];
+        if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
+        if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
+    }
+    __syncthreads();
 
     for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
         const long long env0 = tile * epw;
@@ -339,7 +329,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        const int px = (int)cf.pos.x, py = (int)cf.pos.y, dx = cf.dir.x, dy = cf.dir.y, di = cf.di, inv = cf.inv, t = cf.t;
+        const int px = (int)cf.pos.x, py = (int)cf.pos.y, di = cf.di, inv = cf.inv, t = cf.t;
+        const int dx = (int)(signed char)(cf.dir & 0xffu), dy = (int)(signed char)(cf.dir >> 8);
         const int act = clampi(cf.act, 0, 5);
         __syncwarp();
 
@@ -504,16 +495,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         {
             const int urg = (p.max_steps - t_out) < 40;                                       // :311
             if (active) s_ap[lane] = (uint32_t)urg;
-            if (bulk_pending) {   // the previous tile's bulk copies must be COMPLETE: staging is reused, obs1 is patched
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (bulk_pending) {   // the previous tile's obs1 copy must have finished READING the staging buffer
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 bulk_pending = false;
                 __syncwarp();
-                apply_patch();
             }
             // (4a) base image: the layout's static observation (no agents, empty pots), 16 bytes per lane-step
             {
                 const int n_chunks = (n_valid * env_bytes + 15) >> 4;
-                const int phase = (int)(((env0 % p.tmpl_k) * (long long)env_bytes) >> 4);
+                const int phase = (((int)env0 & (p.tmpl_k - 1)) * env_bytes) >> 4;       // tmpl_k is a power of two
                 uint4 *dst = reinterpret_cast<uint4 *>(stage);
                 int src = phase + lane;
                 src -= (int)fastdiv((unsigned)src, p.magic_tc) * p.tmpl_chunks;
@@ -554,30 +544,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
             }
             const size_t obs_off = (size_t)env0 * env_bytes;
             // this lane's agent cell as agent_1 sees it: "which" flipped (agent_1 is the viewer)
-            patch_valid = active;
-            patch_off = ((size_t)env * C + (size_t)(ny * w + nx)) * OC_OBS_CHANNELS;
-            patch_code = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
+            const int code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
+            const int my_cell = es * C + ny * w + nx;
             if (p.bulk_ok && n_valid == epw) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
+                if (active) stage_record(my_cell, code_v1);
+                if (urg && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 bulk_pending = true;
             } else {
-                // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular, patch right away
+                // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular
                 __syncwarp();
                 const int nb = n_valid * env_bytes;   // even
                 const unsigned short *h0 = reinterpret_cast<const unsigned short *>(stage);
                 unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + obs_off);
                 unsigned short *g1 = reinterpret_cast<unsigned short *>(p.obs1 + obs_off);
-                for (int k = lane; k < (nb >> 1); k += 32) { const unsigned short v = h0[k]; g0[k] = v; g1[k] = v; }
+                for (int k = lane; k < (nb >> 1); k += 32) g0[k] = h0[k];
                 __syncwarp();
-                apply_patch();
+                if (active) stage_record(my_cell, code_v1);
+                if (urg && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
+                __syncwarp();
+                for (int k = lane; k < (nb >> 1); k += 32) g1[k] = h0[k];
             }
         }
 
@@ -655,11 +656,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) oc_env_kernel(const __grid_
         }
         __syncwarp();
     }
-    if (bulk_pending) {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncwarp();
-        apply_patch();
-    }
+    if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 
@@ -788,6 +785,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
     kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = H.tmpl_chunks * 16;
+    kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
@@ -958,12 +956,12 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // tile shape: the largest envs-per-warp that still leaves >= 4 CTAs (16 warps) resident per SM, subject to the
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
-    const int kHdrBytesHost = kHdrFixed + L.tmpl_chunks * 16;
+    const int kHdrBytesHost = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + L.tmpl_chunks * 16;
     auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     int epw = 0;
     for (int e = 16; e >= 2; e >>= 1)
-        if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap / 4) { epw = e; break; }
+        if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap / 8) { epw = e; break; }
     if (!epw)
         for (int e = 2; e <= 16; e <<= 1)
             if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap) { epw = e; break; }

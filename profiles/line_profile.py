@@ -31,3 +31,10 @@ tot = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 print("total warp-instr", tot, "samples", ts)
 for ln, (ex, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:ntop]:
     print(f"{ex:>9} {100*ex/tot:5.1f}%  samp {sm:>4} {100*sm/max(ts,1):5.1f}%  L{ln}: {src[ln-1].strip()[:100] if ln else ''}")
+
+# ---- region totals (line ranges given as extra args "name:lo-hi")
+regs = [a for a in sys.argv[6:] if ":" in a]
+for rg in regs:
+    name, lh = rg.split(":"); lo, hi = map(int, lh.split("-"))
+    ex = sum(v[0] for ln, v in agg.items() if ln and lo <= ln <= hi); sm = sum(v[1] for ln, v in agg.items() if ln and lo <= ln <= hi)
+    print(f"REGION {name:14s} L{lo}-{hi}: instr {ex:>10} {100*ex/tot:5.1f}%  samples {sm:>5} {100*sm/max(ts,1):5.1f}%")
