@@ -84,7 +84,8 @@ struct KParams {
     int h, w, C, WP, map_bytes, span_off, span_len, span_words, span_stride, n_pot, max_steps, random_reset, part;
     int agent_cell0, agent_cell1;
     unsigned magic_C, magic_w, magic_sw;
-    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes;
+    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes, nch;
+    unsigned magic_nch;
     unsigned magic_ns, magic_tc;
 };
 
@@ -248,28 +249,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         }
     };
 
-    // cp.async (LDGSTS) of one tile's interior spans into span buffer `b`; word-granular because an env's
-    // maze_map is only byte-aligned relative to its neighbours (map_bytes need not be a multiple of 4)
+    // cp.async (LDGSTS) of one tile's interior spans into span buffer `b`, 16 bytes per lane-op: env `el`'s slot is
+    // filled from the 16-byte-aligned window that covers its span, so the span itself starts `mis` bytes into the
+    // slot, with mis = (address of the span) mod 16.  The few over-read bytes belong to the env's own wall ring.
     const long long tile_stride = (long long)gridDim.x * kWarpsPerCta;
     auto prefetch_spans = [&](long long tl, int b) {
         const long long e0 = tl * epw;
         const int nv = (int)min((long long)epw, p.N - e0);
-        const long long base = e0 * (long long)p.map_bytes + p.span_off;   // byte offset of env e0's span
-        const uint32_t *mw = reinterpret_cast<const uint32_t *>(p.st.maze_map) + (base >> 2);
-        const int r0 = (int)(base & 3);
+        const unsigned char *g0 = p.st.maze_map + e0 * (long long)p.map_bytes + p.span_off;
+        const int m0 = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
         const uint32_t dst0 = smem_u32(smap_buf + b * epw * span_stride);
-        const int total = nv * span_words;
-        int el = (int)fastdiv((unsigned)lane, p.magic_sw), k = lane - el * span_words;
-        int gw = ((r0 + el * p.map_bytes) >> 2) + k;                        // word index relative to mw
-        unsigned so = dst0 + 4u * (unsigned)(el * sstride_w + k);
+        const int total = nv * p.nch;
         for (int f = lane; f < total; f += 32) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(so), "l"(mw + gw) : "memory");
-            k += 32; gw += 32; so += 128u;
-            while (k >= span_words) {
-                k -= span_words; ++el;
-                gw = ((r0 + el * p.map_bytes) >> 2) + k;
-                so = dst0 + 4u * (unsigned)(el * sstride_w + k);
-            }
+            const int el = (int)fastdiv((unsigned)f, p.magic_nch);
+            const int c = f - el * p.nch;
+            const int o = el * p.map_bytes;
+            const int mis = (m0 + o) & 15;
+            if (16 * c < mis + p.span_len)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                             :: "r"(dst0 + (unsigned)(el * span_stride + 16 * c)), "l"(g0 + (o - mis + 16 * c)) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -312,13 +310,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         const bool active = e < n_valid;
         const int es = active ? e : 0;            // idle lanes shadow env 0 of the tile (reads only)
         const long long env = env0 + es;
-        // byte offset (within maze_map) of the tile's first interior span; per-env word misalignment
-        const long long base0 = env0 * (long long)p.map_bytes + p.span_off;
-        const int r0 = (int)(base0 & 3);
+        // first interior byte of the tile in maze_map; a span sits `mis` bytes into its shared-memory slot
+        unsigned char *g_tile = p.st.maze_map + env0 * (long long)p.map_bytes + p.span_off;
+        const int m0 = (int)(reinterpret_cast<uintptr_t>(g_tile) & 15);
         unsigned char *smap = smap_buf + buf * epw * span_stride;
-        uint32_t *smap_w = reinterpret_cast<uint32_t *>(smap);
-        unsigned char *my_span = smap + es * span_stride + ((r0 + es * p.map_bytes) & 3);
-        unsigned char *g_span = p.st.maze_map + env * (long long)p.map_bytes + p.span_off;   // same bytes in HBM
+        unsigned char *my_span = smap + es * span_stride + ((m0 + es * p.map_bytes) & 15);
+        unsigned char *g_span = g_tile + es * p.map_bytes;                                   // same bytes in HBM
 
         // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
         const Fields cf = nf;
@@ -407,11 +404,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                 full_writeback = true;
                 if (MODE == MODE_STEP && p.has_rs) {
                     // multi_agent_env.py:55-59: caller-supplied reset_state replaces reset(key_reset)
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(p.rs.maze_map) + (base0 >> 2);
+                    const unsigned char *rt = p.rs.maze_map + env0 * (long long)p.map_bytes + p.span_off;
                     for (int el = 0; el < n_valid; ++el) {
                         if (!((done_mask >> (2 * el)) & 1u)) continue;
-                        const int wo = (r0 + el * p.map_bytes) >> 2;
-                        for (int k = lane; k < span_words; k += 32) smap_w[el * sstride_w + k] = __ldg(rw + wo + k);
+                        unsigned char *dst = smap + el * span_stride + ((m0 + el * p.map_bytes) & 15);
+                        for (int k = lane; k < p.span_len; k += 32) dst[k] = __ldg(rt + el * p.map_bytes + k);
                     }
                     if (done && active) {
                         const uint2 pp = __ldg(reinterpret_cast<const uint2 *>(p.rs.agent_pos) + env * 2 + ai);
@@ -426,7 +423,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     // template interior for every finished env (warp-cooperative byte copy)
                     for (int el = 0; el < n_valid; ++el) {
                         if (!((done_mask >> (2 * el)) & 1u)) continue;
-                        unsigned char *dst = smap + el * span_stride + ((r0 + el * p.map_bytes) & 3);
+                        unsigned char *dst = smap + el * span_stride + ((m0 + el * p.map_bytes) & 15);
                         for (int k = lane; k < p.span_len; k += 32) dst[k] = __ldg(L->tmpl_span + k);
                     }
                     __syncwarp();
@@ -521,7 +518,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                 for (int f = lane; f < total; f += 32) {
                     const int el = (int)fastdiv((unsigned)f, p.magic_ns);
                     const uint32_t sc = s_scan[f - el * p.n_scan];
-                    const unsigned char *c = smap + el * span_stride + ((r0 + el * p.map_bytes) & 3) + (int)(sc & 0xffffu);
+                    const unsigned char *c = smap + el * span_stride + ((m0 + el * p.map_bytes) & 15) + (int)(sc & 0xffffu);
                     const int o = c[0], st = c[2];
                     if (o == 8 ? (st != 23) : (o != 2 && o != 10))
                         stage_record(el * C + (int)(sc >> 16), (o == 8) ? kCodePot + min(st, 23) : min(o, 10));
@@ -586,13 +583,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         if (MODE != MODE_OBS) {
             __syncwarp();
             if (full_writeback) {   // a reset rewrote whole interiors: store the staged spans (rare: 1 step in max_steps)
-                uint32_t *mw = reinterpret_cast<uint32_t *>(p.st.maze_map) + (base0 >> 2);
-                const int total = n_valid * span_words;
-                int el = (int)fastdiv((unsigned)lane, p.magic_sw), k = lane - el * span_words;
-                for (int f = lane; f < total; f += 32) {
-                    mw[((r0 + el * p.map_bytes) >> 2) + k] = smap_w[el * sstride_w + k];
-                    k += 32;
-                    while (k >= span_words) { k -= span_words; ++el; }
+                for (int el = 0; el < n_valid; ++el) {
+                    const int mis = (m0 + el * p.map_bytes) & 15;
+                    const unsigned char *src = smap + el * span_stride;          // slot and HBM agree modulo 16
+                    unsigned char *dstg = g_tile + el * p.map_bytes - mis;
+                    for (int o = (mis & ~3) + 4 * lane; o < mis + p.span_len; o += 128)
+                        *reinterpret_cast<uint32_t *>(dstg + o) = *reinterpret_cast<const uint32_t *>(src + o);
                 }
             }
             if (active) {
@@ -786,6 +782,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
     kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = H.tmpl_chunks * 16;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
+    kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
@@ -882,7 +879,7 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     L.span_off = (OC_PAD * L.WP + OC_PAD) * 3;
     L.span_len = ((h - 1) * L.WP + w) * 3;
     L.span_words = (L.span_len + 3 + 3) / 4;
-    L.span_stride = L.span_words * 4;
+    L.span_stride = ((L.span_len + 15 + 15) / 16) * 16;   // shared-memory slot: span + up to 15 bytes of misalignment
     L.n_pot = d->n_pot; L.n_goal = d->n_goal;
     L.max_steps = d->max_steps; L.random_reset = d->random_reset ? 1 : 0; L.task_id = d->task_id;
     L.prng_mode = d->prng_mode;
