@@ -96,9 +96,8 @@ def profiled_traffic(layout_name):
 def cpu_rate(lay, args, n_envs, seconds, threads=None, steps=None):
     """env-steps/s of the oracle (OpenMP over envs) on the host cores."""
     from oracle import oracle as orc
-    if threads:
-        orc.set_threads(threads)
-    cores = threads or orc.max_threads()
+    orc.set_threads(threads or os.cpu_count() or 1)
+    cores = orc.max_threads()
     o = orc.Oracle(lay, random_reset=args.random_reset, max_steps=args.max_steps)
     rng = np.random.default_rng(0)
     keys = rng.integers(0, 2**32, (n_envs, 2), dtype=np.uint32)
@@ -129,6 +128,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     lay = get_layout(args)
+    orc.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the other ranks do no work
     cores = orc.max_threads()
     # bounded sample: size each step so that warmup + K steps finish in about a minute
     probe, _, _, _ = cpu_rate(lay, args, 8192, 1.0)
@@ -263,11 +263,11 @@ def run_ours(args):
              "shaped0": torch.empty(N, dtype=torch.float32, device=dev),
              "shaped1": torch.empty(N, dtype=torch.float32, device=dev),
              "done": torch.empty(N, dtype=torch.bool, device=dev)} for _ in range(OBS_SLOTS)]
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    n_act = 16
-    acts = [{"agent_0": torch.randint(0, 6, (N,), dtype=torch.int32, device=dev, generator=g),
-             "agent_1": torch.randint(0, 6, (N,), dtype=torch.int32, device=dev, generator=g)} for _ in range(n_act)]
+    # synthetic policy: i.i.d. uniform actions, re-drawn on the device for every block of GRAPH_STEPS steps
+    # (one graph-safe torch RNG kernel per block; the env never sees the same action tensor twice)
+    torch.manual_seed(1234 + rank)
+    act_buf = torch.zeros((GRAPH_STEPS, 2, N), dtype=torch.int32, device=dev)
+    acts = [{"agent_0": act_buf[i, 0], "agent_1": act_buf[i, 1]} for i in range(GRAPH_STEPS)]
     stats = torch.zeros(8, dtype=torch.int64, device=dev) if args.log_wrapper else None
 
     # per-step subkeys: the callers' `rng, _rng = split(rng)` chain, refreshed for GRAPH_STEPS steps at a time;
@@ -288,10 +288,11 @@ def run_ours(args):
         kw = dict(donate=True, out=outs[slot])
         if args.log_wrapper:
             kw["stats"] = stats
-        _, states[b], _, _, _ = wenv.step(key, states[b], acts[i % n_act], **kw)
+        _, states[b], _, _, _ = wenv.step(key, states[b], acts[i % GRAPH_STEPS], **kw)
 
     def block(n_blocks):
         for _ in range(n_blocks):
+            act_buf.random_(0, 6)
             launch_chain()
             for i in range(GRAPH_STEPS):
                 one_step(i)
@@ -406,6 +407,7 @@ def run_ours(args):
                              f"{OBS_SLOTS * 2 * N * h * w * 26 / 1e6:.0f} MB per cycle vs 126 MB L2)",
                        "launch": "CUDA graph of 8 steps replayed" if graph is not None else "eager launches",
                        "keys": "per-step subkeys from the split chain; per-env split fused in the kernel",
+                       "actions": "i.i.d. uniform {0..5}, re-drawn on the device every 8 steps inside the timed region",
                        "log_wrapper": bool(args.log_wrapper), "parallelism": f"env-sharded x{world}, no per-step comms"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
     if stats is not None:

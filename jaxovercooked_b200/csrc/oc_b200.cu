@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         return f;
     };
     long long tile = (long long)blockIdx.x * kWarpsPerCta + warp;
+    int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // this lane's share of oc_step_extras.stats
     int buf = 0;
     Fields nf;
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
@@ -488,6 +489,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
             }
         }
 
+        // LogWrapper trackers of this agent: requested here so the loads overlap the observation phase
+        float lw_er = 0.f, lw_el = 0.f, lw_rr = 0.f, lw_rl = 0.f;
+        if (MODE == MODE_STEP && p.ex.episode_returns && active) {
+            const long long j = env * 2 + ai;
+            lw_er = p.ex.episode_returns[j]; lw_el = p.ex.episode_lengths[j];
+            lw_rr = p.ex.returned_episode_returns[j]; lw_rl = p.ex.returned_episode_lengths[j];
+        }
+
         // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
         {
             const int urg = (p.max_steps - t_out) < 40;                                       // :311
@@ -609,12 +618,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     if (p.ex.episode_returns) {   // wrappers/baselines.py:90-106, this lane = agent ai
                         const long long j = env * 2 + ai;
                         const float keep = done ? 0.f : 1.f, dn = done ? 1.f : 0.f;
-                        const float nr = p.ex.episode_returns[j] + (float)rew;
-                        const float nl = p.ex.episode_lengths[j] + 1.f;
+                        const float nr = lw_er + (float)rew;
+                        const float nl = lw_el + 1.f;
                         p.ex.episode_returns[j] = nr * keep;
                         p.ex.episode_lengths[j] = nl * keep;
-                        const float rr = p.ex.returned_episode_returns[j] * keep + nr * dn;
-                        const float rl = p.ex.returned_episode_lengths[j] * keep + nl * dn;
+                        const float rr = lw_rr * keep + nr * dn;
+                        const float rl = lw_rl * keep + nl * dn;
                         p.ex.returned_episode_returns[j] = rr;
                         p.ex.returned_episode_lengths[j] = rl;
                         if (p.ex.returned_episode) p.ex.returned_episode[j] = (uint8_t)done;
@@ -623,34 +632,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                         p.ex.returned_episode[env * 2 + ai] = (uint8_t)done;
                     }
                 }
-                if (p.ex.stats) {   // exact integer partial sums, one atomic per warp and only when non-zero
-                    int v_done = (active && ai == 0 && done) ? 1 : 0;
-                    int v_rew = (active && ai == 0) ? rew : 0;
-                    int v_s0 = (active && ai == 0) ? shaped : 0;
-                    int v_s1 = (active && ai == 1) ? shaped : 0;
-                    #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        v_done += __shfl_xor_sync(0xffffffffu, v_done, o);
-                        v_rew += __shfl_xor_sync(0xffffffffu, v_rew, o);
-                        v_s0 += __shfl_xor_sync(0xffffffffu, v_s0, o);
-                        v_s1 += __shfl_xor_sync(0xffffffffu, v_s1, o);
-                        st_rr += __shfl_xor_sync(0xffffffffu, st_rr, o);
-                        st_rl += __shfl_xor_sync(0xffffffffu, st_rl, o);
-                    }
-                    if (lane == 0) {
-                        unsigned long long *s = reinterpret_cast<unsigned long long *>(p.ex.stats);
-                        if (v_done) atomicAdd(s + 0, (unsigned long long)v_done);
-                        if (v_rew) atomicAdd(s + 1, (unsigned long long)v_rew);
-                        if (v_s0) atomicAdd(s + 2, (unsigned long long)v_s0);
-                        if (v_s1) atomicAdd(s + 3, (unsigned long long)v_s1);
-                        if (st_rr) atomicAdd(s + 4, (unsigned long long)st_rr);
-                        if (st_rl) atomicAdd(s + 5, (unsigned long long)st_rl);
-                        atomicAdd(s + 6, (unsigned long long)n_valid);
-                    }
+                if (p.ex.stats && active) {
+                    if (ai == 0) { acc_done += done ? 1 : 0; acc_rew += rew; acc_s0 += shaped; acc_rr += st_rr; acc_rl += st_rl; }
+                    else acc_s1 += shaped;
                 }
             }
         }
         __syncwarp();
+    }
+    if (MODE == MODE_STEP && p.ex.stats) {   // exact integer sums: one atomic per warp and counter, only when non-zero
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_done += __shfl_xor_sync(0xffffffffu, acc_done, o);
+            acc_rew += __shfl_xor_sync(0xffffffffu, acc_rew, o);
+            acc_s0 += __shfl_xor_sync(0xffffffffu, acc_s0, o);
+            acc_s1 += __shfl_xor_sync(0xffffffffu, acc_s1, o);
+            acc_rr += __shfl_xor_sync(0xffffffffu, acc_rr, o);
+            acc_rl += __shfl_xor_sync(0xffffffffu, acc_rl, o);
+        }
+        if (lane == 0) {
+            unsigned long long *sp = reinterpret_cast<unsigned long long *>(p.ex.stats);
+            if (acc_done) atomicAdd(sp + 0, (unsigned long long)acc_done);
+            if (acc_rew) atomicAdd(sp + 1, (unsigned long long)acc_rew);
+            if (acc_s0) atomicAdd(sp + 2, (unsigned long long)acc_s0);
+            if (acc_s1) atomicAdd(sp + 3, (unsigned long long)acc_s1);
+            if (acc_rr) atomicAdd(sp + 4, (unsigned long long)acc_rr);
+            if (acc_rl) atomicAdd(sp + 5, (unsigned long long)acc_rl);
+            if (blockIdx.x == 0 && warp == 0) atomicAdd(sp + 6, (unsigned long long)p.N);   // every env stepped once
+        }
     }
     if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
