@@ -498,6 +498,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         }
 
         // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
+        bool obs1_pending = false;
+        int code_v1 = 0, my_cell = 0, urg_lane = 0;
+        const size_t obs_off = (size_t)env0 * env_bytes;
         {
             const int urg = (p.max_steps - t_out) < 40;                                       // :311
             if (active) s_ap[lane] = (uint32_t)urg;
@@ -548,10 +551,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     }
                 }
             }
-            const size_t obs_off = (size_t)env0 * env_bytes;
             // this lane's agent cell as agent_1 sees it: "which" flipped (agent_1 is the viewer)
-            const int code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
-            const int my_cell = es * C + ny * w + nx;
+            code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
+            my_cell = es * C + ny * w + nx;
+            urg_lane = urg;
             if (p.bulk_ok && n_valid == epw) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -559,19 +562,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
-                __syncwarp();
-                if (active) stage_record(my_cell, code_v1);
-                if (urg && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                bulk_pending = true;
+                obs1_pending = true;      // issued after the state write-back below, which hides the engine's read
             } else {
                 // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular
                 __syncwarp();
@@ -637,6 +629,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     else acc_s1 += shaped;
                 }
             }
+        }
+        if (obs1_pending) {   // agent_1's view: re-stage the two agent cells once the engine has read the image
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            if (active) stage_record(my_cell, code_v1);
+            if (urg_lane && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            bulk_pending = true;
         }
         __syncwarp();
     }
