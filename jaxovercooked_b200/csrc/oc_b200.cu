@@ -290,12 +290,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         }
         return f;
     };
-    long long tile = (long long)blockIdx.x * kWarpsPerCta + warp;
-    int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // this lane's share of oc_step_extras.stats
-    int buf = 0;
-    Fields nf;
-    if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
-    // CTA-shared tables are fetched while the first tile's state is already in flight
+    // Programmatic dependent launch: let the next kernel in the stream start its own prologue now, fetch the
+    // CTA-shared tables (read-only layout data) while the previous kernel may still be draining, and only then
+    // wait for the previous kernel's memory to be visible before touching any environment state.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     {
         const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
         for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
@@ -303,6 +301,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
         if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    long long tile = (long long)blockIdx.x * kWarpsPerCta + warp;
+    int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // this lane's share of oc_step_extras.stats
+    int buf = 0;
+    Fields nf;
+    if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
     __syncthreads();
 
     for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
@@ -817,8 +821,19 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
         const long long k = (want + resident - 1) / resident;
         ctas = (want + k - 1) / k;
     }
-    oc_env_kernel<MODE><<<(unsigned)ctas, kWarpsPerCta * 32, lay->smem_bytes, stream>>>(kp);
-    return cudaGetLastError() == cudaSuccess ? OC_OK : fail_cuda();
+    static const bool use_pdl = [] { const char *e = std::getenv("OC_B200_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kWarpsPerCta * 32);
+    cfg.dynamicSmemBytes = (size_t)lay->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, oc_env_kernel<MODE>, kp) == cudaSuccess ? OC_OK : fail_cuda();
 }
 
 }  // namespace
