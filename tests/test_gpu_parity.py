@@ -297,3 +297,67 @@ def test_full_size_cramped_room_65536():
     o0 = obs["agent_0"].cpu().numpy()
     assert (o0[..., 0].sum(axis=(1, 2)) == 1).all() and (o0[..., 1].sum(axis=(1, 2)) == 1).all()
     assert (o0[..., [13, 17, 19, 24]] == 0).all() and o0.max() <= 19
+
+
+def _big_run(lay, *, N, T, random_reset, seed, full_at, prefix=256, prefix_every=16, max_steps=400):
+    """Caller recipe (IPPO_CL.py:477,533-538) at benchmark sizes: all envs compared at `full_at`, a prefix often."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    from oracle import prng
+    env = ocb.make("overcooked", layout=lay, random_reset=random_reset, max_steps=max_steps)
+    ref = orc.Oracle(lay, random_reset=random_reset, max_steps=max_steps)
+    rng, rng_np = ocr.PRNGKey(seed), prng.PRNGKey(seed)
+    arng = np.random.default_rng(seed)
+    ks = ocr.split(rng, 2); rng, sub = ks[0].clone(), ks[1]
+    obs, st = env.reset(ocr.split(sub, N))
+    kn = prng.split(rng_np); rng_np, subn = kn[0], kn[1]
+    (r0, r1), rst = ref.reset(prng.split(subn, N))
+    assert_same(obs["agent_0"].cpu().numpy(), r0, "reset obs0")
+    gh.compare_state(st, rst, "reset")
+    out = ref.alloc_out(N)
+    subs = ocr.split_chain(rng, T)                       # the whole `rng, _rng = split(rng)` chain in one kernel
+    for t in range(1, T + 1):
+        a = arng.integers(0, 6, (N, 2)).astype(np.int32)
+        obs, st, rew, done, info = env.step(ocr.LazySplit(subs[t - 1], N), st,
+                                            {"agent_0": gh.to_dev(a[:, 0]), "agent_1": gh.to_dev(a[:, 1])}, donate=True)
+        kn = prng.split(rng_np); rng_np, subn = kn[0], kn[1]
+        (r0, r1), rr, s0, s1, dd = ref.step(prng.split(subn, N), rst, a[:, 0], a[:, 1], out=out)
+        if t in full_at:
+            assert_same(obs["agent_0"].cpu().numpy(), r0, f"t={t} obs0 (all envs)")
+            assert_same(obs["agent_1"].cpu().numpy(), r1, f"t={t} obs1 (all envs)")
+            gh.compare_state(st, rst, f"t={t} (all envs)")
+            assert_same(done["__all__"].cpu().numpy(), dd, f"t={t} done")
+            assert_same(info["shaped_reward"]["agent_0"].cpu().numpy(), s0, f"t={t} shaped0")
+        elif t % prefix_every == 0:
+            assert_same(obs["agent_0"][:prefix].cpu().numpy(), r0[:prefix], f"t={t} obs0 (prefix)")
+            assert_same(obs["agent_1"][:prefix].cpu().numpy(), r1[:prefix], f"t={t} obs1 (prefix)")
+            assert_same(st.maze_map[:prefix].cpu().numpy(), rst["maze_map"][:prefix], f"t={t} maze_map (prefix)")
+        assert_same(rew["agent_0"].cpu().numpy(), rr, f"t={t} reward")
+
+
+def test_config1_16_envs_400_steps_logwrapper():
+    """BASELINE.json configs[0]: cramped_room, 16 envs, LogWrapper, 400-step episodes, seed 30."""
+    from jaxovercooked_b200.layouts import overcooked_layouts
+    _rollout_compare(overcooked_layouts["cramped_room"], random_reset=False, max_steps=400, N=16, T=402, seed=30,
+                     every=1, log=True)
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_config3_cl_sequence_32768_envs(idx):
+    """BASELINE.json configs[2], one GPU's share: each padded 5x9 CL layout, 32,768 envs, across the auto-reset."""
+    from jaxovercooked_b200.layouts import cl_sequence_padded
+    name, lay = list(cl_sequence_padded().items())[idx]
+    _big_run(lay, N=32768, T=404, random_reset=False, seed=idx, full_at=(1, 399, 400, 401, 404))
+
+
+def test_config5_stress_10x10_random_reset_65536():
+    """BASELINE.json configs[4]: padded 10x10 layout, random_reset=True, 65,536 envs, across the auto-reset."""
+    from jaxovercooked_b200.layouts import overcooked_layouts
+    _big_run(overcooked_layouts["easy_layout_padded"], N=65536, T=70, random_reset=True, seed=9,
+             full_at=(1, 59, 60, 61, 70), max_steps=60)
+
+
+def test_config5_stress_9x11_random_reset():
+    from jaxovercooked_b200.layouts import overcooked_layouts
+    _big_run(overcooked_layouts["bottleneck_large"], N=16384 + 37, T=45, random_reset=True, seed=10,
+             full_at=(1, 29, 30, 31, 45), max_steps=30)
