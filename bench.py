@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--random-reset", action="store_true")
     ap.add_argument("--max-steps", type=int, default=400)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--e2e-steps", type=int, default=300)
+    ap.add_argument("--e2e-steps", type=int, default=4000)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
@@ -337,47 +337,43 @@ def run_ours(args):
     launches_per_block = GRAPH_STEPS + 1
     gpu_launches = (K // GRAPH_STEPS) * launches_per_block
 
-    # ---- e2e: the public API with HOST buffers; H2D of the actions and D2H of rewards/shaped/dones every step
-    Ke = max(8, min(args.e2e_steps, args.steps))
-    h_act = [torch.randint(0, 6, (2, N), dtype=torch.int32).pin_memory() for _ in range(8)]
-    h_res = {k: torch.empty(N, dtype=dt).pin_memory() for k, dt in (("reward", torch.float32), ("shaped0", torch.float32),
-                                                                   ("shaped1", torch.float32), ("done", torch.bool))}
-    d_act = torch.empty((2, N), dtype=torch.int32, device=dev)
-    e_rng = rngs[1 % R]
-
-    def e2e_step(i):
-        b, slot = i % R, i % OBS_SLOTS
-        d_act.copy_(h_act[i % 8], non_blocking=True)
-        ks = ocr.split(e_rng, 2)
-        e_rng.copy_(ks[0])
-        key = ocr.LazySplit(ks[1], n_global, first, N)
-        _, states[b], rew, done, info = env.step(key, states[b].env_state if args.log_wrapper else states[b],
-                                                 {"agent_0": d_act[0], "agent_1": d_act[1]}, donate=True, out=outs[slot])
-        h_res["reward"].copy_(rew["agent_0"], non_blocking=True)
-        h_res["shaped0"].copy_(info["shaped_reward"]["agent_0"], non_blocking=True)
-        h_res["shaped1"].copy_(info["shaped_reward"]["agent_1"], non_blocking=True)
-        h_res["done"].copy_(done["__all__"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the step's result before acting again
-
+    # ---- e2e: the C-ABI call with HOST buffers (oc_step_host through env.host_stepper): every step copies that
+    # step's actions from pinned host memory to the device and the step's rewards / shaped rewards / dones back to
+    # pinned host memory.  The R env batches run on R streams, so one batch's copies overlap another's kernel; the
+    # host waits for a batch's previous results before it reuses that batch's buffers.
     e2e = None
     if not args.log_wrapper:
-        for i in range(5):
-            e2e_step(i)
+        Ke = max(2 * R, min(args.e2e_steps, max(args.steps, 2 * R)))
         torch.cuda.synchronize()
+        steppers = [env.host_stepper(states[b], n_global, first) for b in range(R)]
+        h_pool = [torch.randint(0, 6, (2, N), dtype=torch.int32).pin_memory() for _ in range(16)]
+        e_subs = ocr.split_chain(rngs[1 % R], Ke + 2 * R)
+        torch.cuda.synchronize()
+
+        def e2e_run(i0, n):
+            for i in range(i0, i0 + n):
+                st_ = steppers[i % R]
+                st_.wait()                                   # results of this batch's previous step are on the host
+                st_.step(e_subs[i], h_pool[i % 16])
+
+        e2e_run(0, 2 * R)
+        for s_ in steppers:
+            s_.wait()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for i in range(Ke):
-            e2e_step(i)
-        torch.cuda.synchronize()
+        e2e_run(2 * R, Ke)
+        for s_ in steppers:
+            s_.wait()
         dt = time.perf_counter() - t0
         tm = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e = {"value": n_global * Ke / float(tm.item()), "unit": UNIT, "h2d_bytes_per_step": 8 * N,
                "d2h_bytes_per_step": 13 * N, "steps": Ke,
-               "note": "env.step through the host mirror/C ABI; actions from pinned host memory, rewards+shaped+dones "
-                       "read back every step; observations stay on the device for the learner, as in the reference"}
+               "note": "oc_step_host (C ABI, host buffers) via env.host_stepper: actions from pinned host memory in, "
+                       "rewards+shaped+dones to pinned host memory out, every step; observations stay on the device for "
+                       f"the learner, as in the reference; {R} env batches pipelined on {R} streams"}
 
     if rank != 0:
         if world > 1:

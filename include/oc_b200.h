@@ -150,6 +150,17 @@ int oc_step(const oc_layout *layout, int64_t N, const uint32_t *keys, oc_state i
             uint8_t *obs0, uint8_t *obs1, float *reward, float *shaped0, float *shaped1, uint8_t *done,
             const oc_step_extras *extras, void *stream);
 
+/* oc_step for a caller whose policy lives on the HOST: actions come from host memory and the step's results go
+ * back to host memory, all enqueued on `stream` (H2D copy, step kernel, D2H copy; nothing synchronises).
+ *   h_actions  HOST  i32[2,N]  (row 0 = agent_0, row 1 = agent_1); pinned memory makes the copies asynchronous
+ *   h_results  HOST  13*N bytes: reward f32[N] | shaped0 f32[N] | shaped1 f32[N] | done u8[N]
+ *   d_scratch  DEVICE 21*N bytes, 16-byte aligned (device copies of the two blocks above); N % 4 == 0
+ *   state      stepped in place; observations stay on the device (obs0/obs1), where the learner consumes them.
+ * Different env batches on different streams overlap their copies with each other's kernels. */
+int oc_step_host(const oc_layout *layout, int64_t N, const uint32_t *keys, oc_state state,
+                 const int32_t *h_actions, void *h_results, void *d_scratch, uint8_t *obs0, uint8_t *obs1,
+                 const oc_step_extras *extras, void *stream);
+
 /* env.get_obs under vmap: overcooked.py:250-364. */
 int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream);
 

@@ -47,7 +47,7 @@ class LayoutInfo(C.Structure):
 
 
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
-           "oc_reset", "oc_step", "oc_get_obs", "oc_prng_split", "oc_prng_chain")
+           "oc_reset", "oc_step", "oc_step_host", "oc_get_obs", "oc_prng_split", "oc_prng_chain")
 
 _lib = None
 
@@ -85,6 +85,9 @@ def load():
     lib.oc_step.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p,
                             C.POINTER(StatePtrs), StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.POINTER(StepExtras), C.c_void_p]
+    lib.oc_step_host.restype = C.c_int
+    lib.oc_step_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.POINTER(StepExtras), C.c_void_p]
     lib.oc_prng_split.restype = C.c_int
     lib.oc_prng_split.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.oc_prng_chain.restype = C.c_int

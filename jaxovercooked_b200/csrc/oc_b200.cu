@@ -1102,6 +1102,24 @@ int oc_step(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state in, 
     return launch_env<MODE_STEP>(lay, kp, stream);
 }
 
+int oc_step_host(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state state, const int32_t *h_actions,
+                 void *h_results, void *d_scratch, uint8_t *obs0, uint8_t *obs1, const oc_step_extras *extras,
+                 void *stream_) {
+    if (!lay || N < 0 || !h_actions || !h_results || !d_scratch) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    if (!aligned_to(d_scratch, 16) || (N & 3)) return OC_ERR_ALIGNMENT;   // keeps every packed sub-array 4-byte aligned
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    unsigned char *d = static_cast<unsigned char *>(d_scratch);
+    int32_t *d_act = reinterpret_cast<int32_t *>(d);                 // [2,N]
+    float *d_res = reinterpret_cast<float *>(d + 8 * N);             // reward | shaped0 | shaped1 (f32[N] each) | done u8[N]
+    if (cudaMemcpyAsync(d_act, h_actions, (size_t)8 * N, cudaMemcpyHostToDevice, stream) != cudaSuccess) return fail_cuda();
+    const int rc = oc_step(lay, N, keys, state, d_act, d_act + N, nullptr, state, obs0, obs1, d_res, d_res + N,
+                           d_res + 2 * N, reinterpret_cast<uint8_t *>(d_res + 3 * N), extras, stream_);
+    if (rc != OC_OK) return rc;
+    if (cudaMemcpyAsync(h_results, d_res, (size_t)13 * N, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return fail_cuda();
+    return OC_OK;
+}
+
 int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first, int64_t count, uint32_t *out,
                   void *stream_) {
     if (!key || !out || num < 1 || first < 0 || count < 0 || first + count > num || num > 0x7fffffffll)

@@ -261,6 +261,13 @@ class Overcooked:
         infos = {"shaped_reward": {"agent_0": sh0, "agent_1": sh1}}            # :125, :133
         return obs, new_state, rewards, dones, infos
 
+    # ------------------------------------------------------------------ host-policy fast path
+    def host_stepper(self, state, n_global=None, first=0, stream=None):
+        """Bind one env batch for repeated `oc_step_host` calls: actions arrive in pinned host memory, rewards /
+        shaped rewards / dones are written to pinned host memory, observations and state stay on the device.
+        Everything is enqueued on `stream` (default: a new stream), so several batches overlap copy and compute."""
+        return HostStepper(self, state, n_global, first, stream)
+
     def get_obs(self, state):
         """overcooked.py:250-364."""
         batch = tuple(state.time.shape)
@@ -306,6 +313,55 @@ class Overcooked:
                 "goal_pos": Box(0, max(w, h), (2,), torch.uint32),
                 "maze_map": Box(0, 255, (w + v, h + v, 3), torch.uint32),
                 "time": Discrete(self.max_steps), "terminal": Discrete(2)}
+
+
+class HostStepper:
+    """One env batch bound to `oc_step_host` (include/oc_b200.h): a single C call per step enqueues the H2D copy of
+    the actions, the in-place step, and the D2H copy of the results.  `actions` is the pinned int32[2,N] host
+    tensor to fill before `step()`; after `wait()` the pinned views `reward / shaped0 / shaped1 / done` hold the
+    step's results.  Per-env keys are derived in the kernel from `split(key, n_global)[first + i]`."""
+
+    def __init__(self, env, state, n_global=None, first=0, stream=None):
+        batch = tuple(state.time.shape)
+        if len(batch) != 1 or batch[0] % 4:
+            raise ValueError("host_stepper needs a 1-D batch whose size is a multiple of 4")
+        self.env, self.state, self.n = env, state, batch[0]
+        self.n_global = self.n if n_global is None else int(n_global)
+        self.first = int(first)
+        n, dev = self.n, env.device
+        self.stream = torch.cuda.Stream(dev) if stream is None else stream
+        self.actions = torch.zeros((2, n), dtype=torch.int32).pin_memory()
+        self._results = torch.zeros(13 * n, dtype=torch.uint8).pin_memory()
+        self.reward = self._results[:4 * n].view(torch.float32)
+        self.shaped0 = self._results[4 * n:8 * n].view(torch.float32)
+        self.shaped1 = self._results[8 * n:12 * n].view(torch.float32)
+        self.done = self._results[12 * n:].view(torch.bool)
+        self._scratch = torch.empty(21 * n + 16, dtype=torch.uint8, device=dev)
+        self.obs = {"agent_0": torch.empty((n, env.height, env.width, N_CHANNELS), dtype=torch.uint8, device=dev),
+                    "agent_1": torch.empty((n, env.height, env.width, N_CHANNELS), dtype=torch.uint8, device=dev)}
+        self._sp = env._state_ptrs(state, batch)
+        self._ex = _lib.StepExtras()
+        self._event = torch.cuda.Event()
+        self._fn = env._lib.oc_step_host
+        self._stream_ptr = C.c_void_p(self.stream.cuda_stream)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+
+    def step(self, key, actions=None):
+        """Enqueue one step; `key` is the step's subkey (uint32[2] CUDA tensor), split per env inside the kernel.
+        `actions`: a pinned int32[2,N] host tensor to use instead of `self.actions` (no host-side copy)."""
+        ex = self._ex
+        act = self.actions if actions is None else actions
+        self._act_keepalive = act
+        ex.split_key, ex.split_num, ex.split_first = key.data_ptr(), self.n_global, self.first
+        self._key_keepalive = key
+        rc = self._fn(self.env._handle, self.n, None, self._sp, act.data_ptr(), self._results.data_ptr(),
+                      self._scratch.data_ptr(), self.obs["agent_0"].data_ptr(), self.obs["agent_1"].data_ptr(),
+                      C.byref(ex), self._stream_ptr)
+        _lib.check(rc, "oc_step_host")
+        self._event.record(self.stream)
+
+    def wait(self):
+        self._event.synchronize()
 
 
 registered_envs = ["overcooked"]

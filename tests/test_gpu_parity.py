@@ -361,3 +361,30 @@ def test_config5_stress_9x11_random_reset():
     from jaxovercooked_b200.layouts import overcooked_layouts
     _big_run(overcooked_layouts["bottleneck_large"], N=16384 + 37, T=45, random_reset=True, seed=10,
              full_at=(1, 29, 30, 31, 45), max_steps=30)
+
+
+def test_step_host_matches_device_step():
+    """oc_step_host (host action / result buffers) gives exactly what oc_step gives."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    lay = ocb.overcooked_layouts["counter_circuit"]
+    env = ocb.make("overcooked", layout=lay, random_reset=True, max_steps=7)
+    N = 1000
+    _, st_a = env.reset(ocr.split(ocr.PRNGKey(1), N))
+    st_b = st_a.clone()
+    hs = env.host_stepper(st_b)
+    subs = ocr.split_chain(ocr.PRNGKey(2), 20)
+    torch.cuda.synchronize()
+    for t in range(20):
+        a = torch.randint(0, 6, (2, N), dtype=torch.int32)
+        hs.actions.copy_(a)
+        hs.step(subs[t])
+        d = a.cuda()
+        obs, st_a, rew, done, info = env.step(ocr.LazySplit(subs[t], N), st_a, {"agent_0": d[0], "agent_1": d[1]}, donate=True)
+        hs.wait()
+        torch.cuda.synchronize()
+        assert torch.equal(hs.obs["agent_0"], obs["agent_0"]) and torch.equal(hs.obs["agent_1"], obs["agent_1"])
+        assert torch.equal(hs.reward, rew["agent_0"].cpu()) and torch.equal(hs.done, done["__all__"].cpu())
+        assert torch.equal(hs.shaped0, info["shaped_reward"]["agent_0"].cpu())
+        assert torch.equal(hs.shaped1, info["shaped_reward"]["agent_1"].cpu())
+        gh.compare_state(st_b, gh.state_to_numpy(st_a), f"t={t}")
