@@ -84,7 +84,7 @@ struct KParams {
     int h, w, C, WP, map_bytes, span_off, span_len, span_words, span_stride, n_pot, max_steps, random_reset, part;
     int agent_cell0, agent_cell1;
     unsigned magic_C, magic_w, magic_sw;
-    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes, nch;
+    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes, nch, pf_invariant, pf_bytes;
     unsigned magic_nch;
     unsigned magic_ns, magic_tc;
 };
@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + kHdrFixed);   // [n_scan] span offset | cell << 16
     uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed + p.scan_bytes);   // [tmpl_chunks] k envs of the base image
+    uint32_t *s_pf = reinterpret_cast<uint32_t *>(smem + kHdrFixed + p.scan_bytes + p.tmpl_bytes);   // [epw*nch] prefetch plan
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     const int part = p.part;
     const int env_bytes = C * OC_OBS_CHANNELS;
     const int view_bytes = epw * env_bytes;
-    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
+    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.tmpl_bytes + p.pf_bytes + (size_t)warp * p.warp_bytes;
     unsigned char *stage = wbase;                                              // agent_0's view of the tile
     unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
     uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] packed agent state
@@ -260,6 +261,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         const int m0 = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
         const uint32_t dst0 = smem_u32(smap_buf + b * epw * span_stride);
         const int total = nv * p.nch;
+        if (p.pf_invariant) {   // every tile has the same alignment: replay the per-CTA copy plan
+            for (int f = lane; f < total; f += 32) {
+                const uint32_t d = s_pf[f];
+                if (d != 0xffffffffu)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                 :: "r"(dst0 + ((d & 0xffffu) << 4)), "l"(g0 + ((int)(d >> 16) - 16)) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+        }
         for (int f = lane; f < total; f += 32) {
             const int el = (int)fastdiv((unsigned)f, p.magic_nch);
             const int c = f - el * p.nch;
@@ -298,16 +309,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
         for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
         for (int i = tid; i < p.n_scan; i += kWarpsPerCta * 32) s_scan[i] = L->scan[i];
+        if (p.pf_invariant) {
+            const int m0 = (int)((reinterpret_cast<uintptr_t>(p.st.maze_map) + (unsigned)p.span_off) & 15);
+            for (int f = tid; f < epw * p.nch; f += kWarpsPerCta * 32) {
+                const int el = (int)fastdiv((unsigned)f, p.magic_nch);
+                const int c = f - el * p.nch;
+                const int o = el * p.map_bytes;
+                const int mis = (m0 + o) & 15;
+                s_pf[f] = (16 * c < mis + p.span_len)
+                              ? ((unsigned)(el * (span_stride >> 4) + c) | ((unsigned)(o - mis + 16 * c + 16) << 16))
+                              : 0xffffffffu;
+            }
+        }
         if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
         if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
     }
+    __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
     asm volatile("griddepcontrol.wait;" ::: "memory");
     long long tile = (long long)blockIdx.x * kWarpsPerCta + warp;
     int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // this lane's share of oc_step_extras.stats
     int buf = 0;
     Fields nf;
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
-    __syncthreads();
 
     for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
         const long long env0 = tile * epw;
@@ -731,6 +754,7 @@ struct oc_layout {
     int epw;
     int smem_bytes;
     int warp_bytes;
+    int pf_bytes;
     int num_sms;
     mutable int occ[3];   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
@@ -802,6 +826,8 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = H.tmpl_chunks * 16;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
+    kp.pf_bytes = lay->pf_bytes;
+    kp.pf_invariant = (((long long)lay->epw * H.map_bytes) % 16 == 0 && (long long)lay->epw * H.map_bytes + 32 < 65536) ? 1 : 0;
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
@@ -983,24 +1009,26 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // tile shape: the largest envs-per-warp that still leaves >= 4 CTAs (16 warps) resident per SM, subject to the
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
-    const int kHdrBytesHost = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + L.tmpl_chunks * 16;
+    auto pf_bytes_for = [&](int e) { return ((e * (L.span_stride / 16) * 4) + 15) & ~15; };
+    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + L.tmpl_chunks * 16;
     auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     int epw = 0;
     for (int e = 16; e >= 2; e >>= 1)
-        if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap / 8) { epw = e; break; }
+        if (size_ok(e) && kHdrBytesHost0 + pf_bytes_for(e) + kWarpsPerCta * warp_bytes_for(e) <= smem_cap / 8) { epw = e; break; }
     if (!epw)
         for (int e = 2; e <= 16; e <<= 1)
-            if (size_ok(e) && kHdrBytesHost + kWarpsPerCta * warp_bytes_for(e) <= smem_cap) { epw = e; break; }
+            if (size_ok(e) && kHdrBytesHost0 + pf_bytes_for(e) + kWarpsPerCta * warp_bytes_for(e) <= smem_cap) { epw = e; break; }
     if (const char *ev = std::getenv("OC_B200_EPW")) {
         const int v = std::atoi(ev);
         if ((v == 2 || v == 4 || v == 8 || v == 16) && size_ok(v) &&
-            kHdrBytesHost + kWarpsPerCta * warp_bytes_for(v) <= smem_cap) epw = v;
+            kHdrBytesHost0 + pf_bytes_for(v) + kWarpsPerCta * warp_bytes_for(v) <= smem_cap) epw = v;
     }
     if (!epw) { delete lay; return OC_ERR_UNSUPPORTED_LAYOUT; }
     lay->epw = epw;
     lay->warp_bytes = warp_bytes_for(epw);
-    lay->smem_bytes = kHdrBytesHost + kWarpsPerCta * lay->warp_bytes;
+    lay->pf_bytes = pf_bytes_for(epw);
+    lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + kWarpsPerCta * lay->warp_bytes;
     lay->num_sms = prop.multiProcessorCount;
     lay->occ[0] = lay->occ[1] = lay->occ[2] = 0;
     lay->device = device;
