@@ -388,3 +388,27 @@ def test_step_host_matches_device_step():
         assert torch.equal(hs.shaped0, info["shaped_reward"]["agent_0"].cpu())
         assert torch.equal(hs.shaped1, info["shaped_reward"]["agent_1"].cpu())
         gh.compare_state(st_b, gh.state_to_numpy(st_a), f"t={t}")
+
+
+def test_rollout_buffer_is_batchify_layout():
+    """the step writes observations straight into the (T, 2N, h*w*26) agent-major trajectory tensor
+    that baselines/utils.py:48-61 `batchify` + `Transition.obs` build with an extra copy."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    lay = ocb.overcooked_layouts["cramped_room"]
+    env = ocb.make("overcooked", layout=lay, max_steps=9)
+    N, T = 512, 12
+    buf = ocb.RolloutBuffer(env, T, N)
+    _, st = env.reset(ocr.split(ocr.PRNGKey(0), N))
+    st_ref = st.clone()
+    subs = ocr.split_chain(ocr.PRNGKey(1), T)
+    for t in range(T):
+        a = {"agent_0": torch.randint(0, 6, (N,), dtype=torch.int32, device="cuda"),
+             "agent_1": torch.randint(0, 6, (N,), dtype=torch.int32, device="cuda")}
+        _, st, _, _, _ = env.step(ocr.LazySplit(subs[t], N), st, a, donate=True, out=buf.slot(t))
+        obs, st_ref, rew, done, info = env.step(ocr.LazySplit(subs[t], N), st_ref, a, donate=True)
+        batchified = torch.stack([obs["agent_0"], obs["agent_1"]]).reshape(2 * N, -1)      # utils.py:48-61
+        assert torch.equal(buf.batchified_obs(t), batchified)
+        assert torch.equal(buf.reward[t], rew["agent_0"]) and torch.equal(buf.done[t], done["__all__"])
+        assert torch.equal(buf.shaped[t, 1], info["shaped_reward"]["agent_1"])
+    assert buf.batchified_obs().shape == (T, 2 * N, 4 * 5 * 26)
