@@ -73,6 +73,7 @@ struct KParams {
     oc_state rs;
     int has_rs;
     const int32_t *act0, *act1;
+    const unsigned char *tmpl_tile;   // epw back-to-back copies of the layout's static observation (device memory)
     uint8_t *obs0, *obs1;
     float *reward, *shaped0, *shaped1;
     uint8_t *done;
@@ -214,8 +215,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem);                // [0..7] wall, [8..15] blocked
     unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + kHdrFixed);   // [n_scan] span offset | cell << 16
-    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed + p.scan_bytes);   // [tmpl_chunks] k envs of the base image
-    uint32_t *s_pf = reinterpret_cast<uint32_t *>(smem + kHdrFixed + p.scan_bytes + p.tmpl_bytes);   // [epw*nch] prefetch plan
+    uint32_t *s_pf = reinterpret_cast<uint32_t *>(smem + kHdrFixed + p.scan_bytes);   // [epw*nch] prefetch plan
+    // small static images are kept in shared memory and copied by the lanes (tmpl_bytes > 0); large ones are pulled
+    // per tile from global memory by the bulk-copy engine
+    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed + p.scan_bytes + p.pf_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
@@ -224,10 +227,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     const int part = p.part;
     const int env_bytes = C * OC_OBS_CHANNELS;
     const int view_bytes = epw * env_bytes;
-    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.tmpl_bytes + p.pf_bytes + (size_t)warp * p.warp_bytes;
+    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.pf_bytes + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
     unsigned char *stage = wbase;                                              // agent_0's view of the tile
     unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
-    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] packed agent state
+    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] urgency flags
+    const uint32_t tbar = smem_u32(s_ap + 2 * epw);                                    // this warp's mbarrier (8 bytes)
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
     bool bulk_pending = false;
@@ -306,8 +310,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     // wait for the previous kernel's memory to be visible before touching any environment state.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     {
-        const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
-        for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
+        if (p.tmpl_bytes) {
+            const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
+            for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
+        }
         for (int i = tid; i < p.n_scan; i += kWarpsPerCta * 32) s_scan[i] = L->scan[i];
         if (p.pf_invariant) {
             const int m0 = (int)((reinterpret_cast<uintptr_t>(p.st.maze_map) + (unsigned)p.span_off) & 15);
@@ -323,6 +329,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         }
         if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
         if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
+    }
+    // The static observation image of a tile lives in global memory (L2-resident, tile-sized); each tile's staging
+    // buffer is (re)filled from it by ONE bulk asynchronous copy that completes on this warp's mbarrier while the
+    // step logic runs.
+    uint32_t tphase = 0;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -345,6 +359,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         unsigned char *my_span = smap + es * span_stride + ((m0 + es * p.map_bytes) & 15);
         unsigned char *g_span = g_tile + es * p.map_bytes;                                   // same bytes in HBM
 
+        // ------------------------------------------------ (0) refill the staging buffer with the static image
+        if (!p.tmpl_bytes) {
+            if (lane == 0) {
+                if (bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // obs1 of the previous tile
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tbar), "r"(view_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(stage)), "l"(p.tmpl_tile), "r"(view_bytes), "r"(tbar) : "memory");
+            }
+            bulk_pending = false;
+        }
         // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
         const Fields cf = nf;
         if (tile + tile_stride < p.n_tiles) {
@@ -531,17 +555,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         {
             const int urg = (p.max_steps - t_out) < 40;                                       // :311
             if (active) s_ap[lane] = (uint32_t)urg;
-            if (bulk_pending) {   // the previous tile's obs1 copy must have finished READING the staging buffer
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                bulk_pending = false;
-                __syncwarp();
-            }
-            // (4a) base image: the layout's static observation (no agents, empty pots), 16 bytes per lane-step
-            {
+            // (4a) base image
+            if (p.tmpl_bytes) {   // copied by the lanes from shared memory, 16 bytes per lane-step
+                if (bulk_pending) {   // the previous tile's obs1 copy must have finished READING the staging buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    bulk_pending = false;
+                    __syncwarp();
+                }
                 const int n_chunks = (n_valid * env_bytes + 15) >> 4;
-                const int phase = (((int)env0 & (p.tmpl_k - 1)) * env_bytes) >> 4;       // tmpl_k is a power of two
                 uint4 *dst = reinterpret_cast<uint4 *>(stage);
-                int src = phase + lane;
+                int src = lane;                                                         // tiles start on a template period
                 src -= (int)fastdiv((unsigned)src, p.magic_tc) * p.tmpl_chunks;
                 const int step = 32 - (int)fastdiv(32u, p.magic_tc) * p.tmpl_chunks;      // 32 mod tmpl_chunks
                 for (int f = lane; f < n_chunks; f += 32) {
@@ -549,6 +572,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     src += step;
                     if (src >= p.tmpl_chunks) src -= p.tmpl_chunks;
                 }
+            } else {              // wait for the bulk copy issued at the top of the tile
+                uint32_t ok = 0;
+                while (!ok) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(tbar), "r"(tphase) : "memory");
+                }
+                tphase ^= 1u;
             }
             __syncwarp();
             // (4b) cells that can deviate from the base image: counters next to a walkable cell (loose items) and pots
@@ -755,6 +785,8 @@ struct oc_layout {
     int smem_bytes;
     int warp_bytes;
     int pf_bytes;
+    int tmpl_smem_bytes;       // > 0: the static image (tmpl_k copies) is kept in shared memory
+    unsigned char *tmpl_tile;
     int num_sms;
     mutable int occ[3];   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
@@ -816,6 +848,7 @@ template <int MODE>
 int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     const DevLayout &H = lay->host;
     kp.L = lay->dev;
+    kp.tmpl_tile = lay->tmpl_tile;
     kp.epw = lay->epw;
     kp.warp_bytes = lay->warp_bytes;
     kp.h = H.h; kp.w = H.w; kp.C = H.C; kp.WP = H.WP; kp.map_bytes = H.map_bytes; kp.span_off = H.span_off;
@@ -823,7 +856,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
-    kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = H.tmpl_chunks * 16;
+    kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = lay->tmpl_smem_bytes;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
     kp.pf_bytes = lay->pf_bytes;
@@ -1010,8 +1043,9 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
     auto pf_bytes_for = [&](int e) { return ((e * (L.span_stride / 16) * 4) + 15) & ~15; };
-    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + L.tmpl_chunks * 16;
-    auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4) + 15) & ~15; };
+    const int tmpl_smem = (L.tmpl_chunks * 16 <= 4096) ? L.tmpl_chunks * 16 : 0;
+    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + tmpl_smem;
+    auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     int epw = 0;
     for (int e = 16; e >= 2; e >>= 1)
@@ -1028,11 +1062,22 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->epw = epw;
     lay->warp_bytes = warp_bytes_for(epw);
     lay->pf_bytes = pf_bytes_for(epw);
+    lay->tmpl_smem_bytes = tmpl_smem;
     lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + kWarpsPerCta * lay->warp_bytes;
     lay->num_sms = prop.multiProcessorCount;
     lay->occ[0] = lay->occ[1] = lay->occ[2] = 0;
     lay->device = device;
-    if (cudaMalloc(&lay->dev, sizeof(DevLayout)) != cudaSuccess) { delete lay; return fail_cuda(); }
+    {   // tile-sized static observation image
+        const size_t eb = (size_t)C * OC_OBS_CHANNELS;
+        std::vector<unsigned char> img((size_t)epw * eb);
+        for (int k = 0; k < epw; ++k) std::memcpy(img.data() + (size_t)k * eb, L.obs_tmpl, eb);
+        lay->tmpl_tile = nullptr;
+        if (cudaMalloc(&lay->tmpl_tile, img.size()) != cudaSuccess) { delete lay; return fail_cuda(); }
+        if (cudaMemcpy(lay->tmpl_tile, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(lay->tmpl_tile); delete lay; return fail_cuda();
+        }
+    }
+    if (cudaMalloc(&lay->dev, sizeof(DevLayout)) != cudaSuccess) { cudaFree(lay->tmpl_tile); delete lay; return fail_cuda(); }
     if (cudaMemcpy(lay->dev, &L, sizeof(DevLayout), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(lay->dev); delete lay; return fail_cuda();
     }
@@ -1043,6 +1088,7 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
 void oc_layout_destroy(oc_layout *lay) {
     if (!lay) return;
     if (lay->dev) cudaFree(lay->dev);
+    if (lay->tmpl_tile) cudaFree(lay->tmpl_tile);
     delete lay;
 }
 
