@@ -205,7 +205,7 @@ __device__ __forceinline__ Interact interact_cell(int obj, int status, int inv, 
 // ------------------------------------------------------------------------------------------------ kernel
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
     // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
     const int epw = p.epw;
-    const int span_stride = p.span_stride, span_words = p.span_words, sstride_w = p.span_stride >> 2;
+    const int span_stride = p.span_stride;
     const int part = p.part;
     const int env_bytes = C * OC_OBS_CHANNELS;
     const int view_bytes = epw * env_bytes;
