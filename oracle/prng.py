@@ -15,9 +15,11 @@ jax/_src/random.py as of 0.4.25): threefry2x32 (Random123, 20 rounds), `split`, 
     overcooked_environment/overcooked.py:225-228           split, choice(4 items)    == randint(0, 4)
     baselines/IPPO_CL.py:477,535                           split(rng, num_envs)
 
-PARITY STATUS: pinned only by the Random123 threefry2x32 known-answer vectors and the
-`split(PRNGKey(0))` values printed in JAX's own documentation (tests/test_prng.py); no JAX is
-installed in this image, so everything layered above `split` is "parity unpinned" against real JAX.
+PARITY STATUS: no JAX is installed in this image.  Pinned by external known-answer vectors only
+(tests/test_prng.py): Random123 threefry2x32 vectors; the `split(PRNGKey(0))` values printed in JAX's
+documentation (both modes); and `random.normal(PRNGKey(0), (10,))` as printed in JAX's quickstart
+(both modes), which pins `random_bits` and the bits->float mapping.  `randint`'s two-draw combination and
+`choice`'s Gumbel/argsort route have no external vector: they stay "parity unpinned" against real JAX.
 
 Two modes, selected by `partitionable`:
   False (default)  jax_threefry_partitionable=False, the default for jax < 0.5.0 (matches the 0.4.25 hint)

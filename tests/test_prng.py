@@ -79,3 +79,26 @@ def test_integer_choice_equals_float_gumbel_topk(part):
             f = prng.choice_no_replace_p(key, n, 2, free.astype(np.float32), part)
             i = prng.choice_no_replace_p_int(key, n, 2, free, part)
             assert f.tolist() == i.tolist()
+
+
+# jax.random.normal(jax.random.PRNGKey(0), (10,)) as printed in JAX's own quickstart: the older docs (legacy threefry,
+# jax < 0.5) and the current docs (jax_threefry_partitionable=True).  normal = sqrt(2) * erfinv(uniform(-1, 1)), and
+# uniform is the mantissa trick on random_bits(key, 10): an external known-answer for `random_bits` in both modes
+# (counter layout of the legacy mode, y0 ^ y1 of the partitionable mode) and for the bits -> float32 mapping.
+JAX_QUICKSTART_NORMAL = {
+    False: [-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442, -0.67135346, -0.5908641,
+            0.73168886, 0.5673026],
+    True: [1.6226422, 2.0252647, -0.43359444, -0.07861735, 0.1760909, -0.97208923, -0.49529874, 0.4943786,
+           0.6643493, -0.9501635],
+}
+
+
+@pytest.mark.parametrize("part", [False, True])
+def test_random_bits_against_jax_quickstart_normal(part):
+    from scipy.special import erfinv
+    bits = prng.random_bits(prng.PRNGKey(0), 10, part)
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo, hi = np.nextafter(np.float32(-1), np.float32(0)), np.float32(1)
+    u = np.maximum(lo, f * (hi - lo) + lo)                       # jax.random.uniform(key, (10,), minval=lo, maxval=1)
+    x = np.sqrt(2.0) * erfinv(u.astype(np.float64))
+    assert np.allclose(x, JAX_QUICKSTART_NORMAL[part], rtol=0, atol=3e-7)
