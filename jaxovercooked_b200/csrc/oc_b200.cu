@@ -12,18 +12,22 @@
 // Design (DESIGN.md has the long form):
 //   * one WARP owns a tile of `epw` consecutive environments; lanes 2e / 2e+1 are agent_0 / agent_1 of env e.
 //     Movement, collision/swap and the Alice-before-Bob interact ordering are resolved with __shfl_xor_sync
-//     between the two lanes of a pair; whole-warp votes skip the reset and conflict paths.
+//     between the two lanes of a pair; whole-warp votes skip the reset, conflict and urgency paths.  The grid is
+//     persistent and launched with programmatic stream serialization (griddepcontrol), so the next step's
+//     prologue overlaps this step's tail.
 //   * the only part of maze_map that can ever change is the h x w interior; the warp stages the byte span that
-//     covers the interior rows (word-granular, coalesced) in shared memory, updates it there, emits the
-//     observations from it and writes the span back in place.  The constant 4-cell wall ring is never touched.
+//     covers the interior rows with 16-byte cp.async into double-buffered shared memory (prefetching the next
+//     tile), updates it there and mirrors every changed cell to HBM in place.  The constant wall ring is never
+//     touched; whole spans are written back only for envs that reset.
 //   * observations are the HBM roofline term.  Each cell's 26 channel bytes are a pure function of a small
-//     "cell code" (object / pot status / agent x direction x inventory), so a 68-entry record table in shared
-//     memory turns the observation into table copies: one lane assembles a PAIR of cells (52 B = 13 words,
-//     conflict-free in shared memory), both agents' views are staged per tile and leave the SM as two bulk
-//     asynchronous copies (cp.async.bulk.global.shared::cta -- the TMA engine; SASS UBLKCP), i.e. full-line
-//     coalesced writes with no per-thread store instructions.
+//     "cell code" (object / pot status / agent x direction x inventory; 68 records), and almost every cell equals
+//     the layout's static image.  Per tile the staging buffer is filled with that image (lane copy from shared
+//     memory for small images, one TMA bulk load completing on an mbarrier for large ones), the few deviating
+//     cells (pots, items on counters, the two agents, urgency) are re-staged, and the tile leaves the SM as one
+//     bulk asynchronous copy per agent (cp.async.bulk.global.shared::cta; SASS UBLKCP) -- no per-thread stores.
 //   * auto-reset is fused: envs whose episode ended rebuild their interior from a per-layout template and draw
-//     direction / position / pot status / inventory with an in-kernel threefry2x32.
+//     direction / position / pot status / inventory with an in-kernel threefry2x32; per-env keys can be derived
+//     in the kernel from split(key, num)[first + i] for exactly the envs that reset.
 #include "oc_b200.h"
 
 #include <cuda_runtime.h>
@@ -48,11 +52,11 @@ constexpr int kHdrFixed = 64 + 32;   // wall/blocked bitmaps, pot cells; then th
 
 struct DevLayout {
     int h, w, C, WP;
-    int map_bytes, span_off, span_len, span_words, span_stride;
+    int map_bytes, span_off, span_len, span_stride;
     int n_pot, n_goal;
     int max_steps, random_reset, task_id, prng_mode;
     int agent_cell[2];
-    unsigned magic_C, magic_w, magic_sw;      // ceil(2^32 / d) for d = C, w, span_words
+    unsigned magic_C, magic_w;                // ceil(2^32 / d) for d = C, w
     unsigned wall_bits[8], blocked_bits[8];   // wall_map; wall_map | goal cells (movement blocking)
     unsigned short pot_cell[OC_MAX_SPECIAL];
     unsigned short goal_cell[OC_MAX_SPECIAL];
@@ -82,9 +86,9 @@ struct KParams {
     int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
     int warp_bytes; // shared memory per warp
     // scalar copies of the layout, so the hot loop reads them from the constant bank
-    int h, w, C, WP, map_bytes, span_off, span_len, span_words, span_stride, n_pot, max_steps, random_reset, part;
+    int h, w, C, WP, map_bytes, span_off, span_len, span_stride, n_pot, max_steps, random_reset, part;
     int agent_cell0, agent_cell1;
-    unsigned magic_C, magic_w, magic_sw;
+    unsigned magic_C, magic_w;
     int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes, nch, pf_invariant, pf_bytes;
     unsigned magic_nch;
     unsigned magic_ns, magic_tc;
@@ -852,10 +856,10 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.epw = lay->epw;
     kp.warp_bytes = lay->warp_bytes;
     kp.h = H.h; kp.w = H.w; kp.C = H.C; kp.WP = H.WP; kp.map_bytes = H.map_bytes; kp.span_off = H.span_off;
-    kp.span_len = H.span_len; kp.span_words = H.span_words; kp.span_stride = H.span_stride; kp.n_pot = H.n_pot;
+    kp.span_len = H.span_len; kp.span_stride = H.span_stride; kp.n_pot = H.n_pot;
     kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
-    kp.magic_C = H.magic_C; kp.magic_w = H.magic_w; kp.magic_sw = H.magic_sw;
+    kp.magic_C = H.magic_C; kp.magic_w = H.magic_w;
     kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = lay->tmpl_smem_bytes;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
@@ -967,13 +971,12 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     L.map_bytes = (h + 2 * OC_PAD) * L.WP * 3;
     L.span_off = (OC_PAD * L.WP + OC_PAD) * 3;
     L.span_len = ((h - 1) * L.WP + w) * 3;
-    L.span_words = (L.span_len + 3 + 3) / 4;
     L.span_stride = ((L.span_len + 15 + 15) / 16) * 16;   // shared-memory slot: span + up to 15 bytes of misalignment
     L.n_pot = d->n_pot; L.n_goal = d->n_goal;
     L.max_steps = d->max_steps; L.random_reset = d->random_reset ? 1 : 0; L.task_id = d->task_id;
     L.prng_mode = d->prng_mode;
     L.agent_cell[0] = d->agent_idx[0]; L.agent_cell[1] = d->agent_idx[1];
-    L.magic_C = magic_of((unsigned)C); L.magic_w = magic_of((unsigned)w); L.magic_sw = magic_of((unsigned)L.span_words);
+    L.magic_C = magic_of((unsigned)C); L.magic_w = magic_of((unsigned)w);
     for (int c = 0; c < C; ++c)
         if (wall[c]) { L.wall_bits[c >> 5] |= 1u << (c & 31); L.blocked_bits[c >> 5] |= 1u << (c & 31); }
     for (int i = 0; i < d->n_goal; ++i) {
