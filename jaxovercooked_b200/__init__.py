@@ -13,7 +13,7 @@ from .layouts import (Layout, overcooked_layouts, layout_grid_to_dict, pad_layou
 __version__ = "0.1.0"
 
 _LAZY = {"Overcooked": "env", "State": "env", "make": "env", "vmap": "env", "registered_envs": "env",
-         "Actions": "env", "LogWrapper": "wrappers", "LogEnvState": "wrappers", "random": None, "env": None,
+         "Actions": "env", "LogWrapper": "wrappers", "LogEnvState": "wrappers", "CTRolloutManager": "wrappers", "random": None, "env": None,
          "wrappers": None, "dist": None, "rollout": None, "RolloutBuffer": "rollout"}
 
 

@@ -61,3 +61,43 @@ class LogWrapper(JaxMARLWrapper):
         info["returned_episode_lengths"] = new_state.returned_episode_lengths
         info["returned_episode"] = returned_episode
         return obs, new_state, reward, done, info
+
+
+class CTRolloutManager(JaxMARLWrapper):
+    """Rollout manager of the Q-learning baselines (reference: jax_marl/wrappers/baselines.py:153-249) for the way
+    the VDN scripts use it -- `CTRolloutManager(LogWrapper(make(...)), batch_size=num_envs, preprocess_obs=False)`
+    (baselines/vdn_mlp.py:339-346): `batch_reset(key)` / `batch_step(key, states, actions)` split `key` into
+    `batch_size` per-env keys (fused into the kernel on the step side), and add the global state
+    `obs["__all__"]` = the two agents' flattened observations side by side (:196) and `reward["__all__"]` = agent_0's
+    reward (:197).  `preprocess_obs=True` (pad + one-hot agent id, :237-249) is not on the Overcooked VDN path and is
+    not provided."""
+
+    def __init__(self, env, batch_size, preprocess_obs=False):
+        super().__init__(env)
+        if preprocess_obs:
+            raise NotImplementedError("preprocess_obs=True is not used by the Overcooked VDN baselines")
+        self.batch_size = int(batch_size)
+        self.training_agents = self.agents
+        self.preprocess_obs = False
+        inner = env
+        while hasattr(inner, "_env"):
+            inner = inner._env
+        self._impl = "threefry_partitionable" if inner.prng_mode else "threefry_legacy"
+
+    def _global_state(self, obs):
+        return torch.cat([obs[a].reshape(self.batch_size, -1) for a in self.agents], dim=-1)
+
+    def batch_reset(self, key):
+        from . import random as jr
+        obs, state = self._env.reset(jr.split(key, self.batch_size, impl=self._impl))
+        obs = dict(obs)
+        obs["__all__"] = self._global_state(obs)
+        return obs, state
+
+    def batch_step(self, key, states, actions, **kw):
+        from . import random as jr
+        obs, states, reward, done, infos = self._env.step(jr.LazySplit(key, self.batch_size), states, actions, **kw)
+        obs, reward = dict(obs), dict(reward)
+        obs["__all__"] = self._global_state(obs)
+        reward["__all__"] = reward[self.training_agents[0]]
+        return obs, states, reward, done, infos

@@ -412,3 +412,28 @@ def test_rollout_buffer_is_batchify_layout():
         assert torch.equal(buf.reward[t], rew["agent_0"]) and torch.equal(buf.done[t], done["__all__"])
         assert torch.equal(buf.shaped[t, 1], info["shaped_reward"]["agent_1"])
     assert buf.batchified_obs().shape == (T, 2 * N, 4 * 5 * 26)
+
+
+def test_ct_rollout_manager_vdn_surface():
+    """CTRolloutManager(LogWrapper(env), batch_size, preprocess_obs=False) as vdn_mlp.py:339-346 uses it."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    from oracle import prng
+    lay = ocb.overcooked_layouts["cramped_room"]
+    B = 300
+    mgr = ocb.CTRolloutManager(ocb.LogWrapper(ocb.make("overcooked", layout=lay, max_steps=6)), batch_size=B)
+    ref = orc.Oracle(lay, max_steps=6)
+    k0 = ocr.PRNGKey(3)
+    obs, st = mgr.batch_reset(k0)
+    (r0, r1), rst = ref.reset(prng.split(prng.PRNGKey(3), B))
+    assert obs["__all__"].shape == (B, 2 * 4 * 5 * 26)
+    assert_same(obs["__all__"].cpu().numpy(), np.concatenate([r0.reshape(B, -1), r1.reshape(B, -1)], 1), "reset __all__")
+    rlog = ref.new_log(B)
+    for t in range(9):
+        a = np.random.default_rng(t).integers(0, 6, (B, 2)).astype(np.int32)
+        kt = ocr.PRNGKey(100 + t)
+        obs, st, rew, done, info = mgr.batch_step(kt, st, {"agent_0": gh.to_dev(a[:, 0]), "agent_1": gh.to_dev(a[:, 1])})
+        (r0, r1), rr, s0, s1, dd = ref.step(prng.split(prng.PRNGKey(100 + t), B), rst, a[:, 0], a[:, 1], log=rlog)
+        assert_same(obs["__all__"].cpu().numpy(), np.concatenate([r0.reshape(B, -1), r1.reshape(B, -1)], 1), f"t={t} __all__")
+        assert_same(rew["__all__"].cpu().numpy(), rr, f"t={t} reward __all__")
+        assert_same(info["returned_episode_returns"].cpu().numpy(), rlog["returned_episode_returns"], f"t={t} returns")
