@@ -31,3 +31,12 @@ def assert_same(a, b, what):
         bad = np.argwhere(a != b)
         raise AssertionError(f"{what}: {len(bad)} mismatches, first at {bad[0].tolist()}: "
                              f"{a[tuple(bad[0])]} vs {b[tuple(bad[0])]}")
+
+
+def crafted_state(g):
+    """Full batched State (numpy dict) of a crafted fixture: dynamic fields from r_*, static ones broadcast."""
+    E = g["r_time"].shape[0]
+    st = {f: np.ascontiguousarray(g["r_" + f]) for f in DYN_FIELDS}
+    for f in STATIC_FIELDS:
+        st[f] = np.ascontiguousarray(np.broadcast_to(g[f], (E,) + g[f].shape))
+    return st

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import DYN_FIELDS, STATIC_FIELDS, LOG_FIELDS, assert_same, golden_cases, load_golden
+from tests.helpers import (DYN_FIELDS, STATIC_FIELDS, LOG_FIELDS, assert_same, crafted_state, golden_cases,
+                           load_golden)
 
 pytestmark = pytest.mark.gpu
 
@@ -28,7 +29,11 @@ def test_cuda_matches_reference_golden(case):
                    task_id=meta["task_id"],
                    prng_impl="threefry_partitionable" if meta["partitionable"] else "threefry_legacy")
     wenv = ocb.LogWrapper(env) if meta["log_wrapper"] else env
-    obs, st = wenv.reset(gh.keys_to_dev(g["reset_keys"]))
+    if meta.get("crafted"):      # hand-built states: oc_get_obs on them, then one oc_step
+        st = gh.numpy_state_to_dev(env, crafted_state(g))
+        obs = env.get_obs(st)
+    else:
+        obs, st = wenv.reset(gh.keys_to_dev(g["reset_keys"]))
     es = st.env_state if meta["log_wrapper"] else st
     assert_same(obs["agent_0"].cpu().numpy(), g["r_obs0"], "reset obs0")
     assert_same(obs["agent_1"].cpu().numpy(), g["r_obs1"], "reset obs1")

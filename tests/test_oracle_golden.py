@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from tests.helpers import DYN_FIELDS, STATIC_FIELDS, LOG_FIELDS, assert_same, golden_cases, load_golden
+from tests.helpers import (DYN_FIELDS, STATIC_FIELDS, LOG_FIELDS, assert_same, crafted_state, golden_cases,
+                           load_golden)
 
 
 @pytest.mark.parametrize("case", golden_cases())
@@ -13,7 +14,11 @@ def test_oracle_matches_reference_trajectory(case):
     g, meta, lay = load_golden(case)
     o = orc.Oracle(lay, random_reset=meta["random_reset"], max_steps=meta["max_steps"], task_id=meta["task_id"],
                    partitionable=meta["partitionable"])
-    (obs0, obs1), st = o.reset(g["reset_keys"])
+    if meta.get("crafted"):      # hand-built states (tests/golden/make_interact_matrix.py): get_obs, then one step
+        st = crafted_state(g)
+        obs0, obs1 = o.get_obs(st)
+    else:
+        (obs0, obs1), st = o.reset(g["reset_keys"])
     assert_same(obs0, g["r_obs0"], "reset obs0")
     assert_same(obs1, g["r_obs1"], "reset obs1")
     for f in DYN_FIELDS:
