@@ -46,7 +46,7 @@ constexpr int kCodePot = 11;
 constexpr int kCodeAgent = 35;
 constexpr int kMaxSpanBytes = ((OC_MAX_DIM - 1) * (OC_MAX_DIM + 2 * OC_PAD) + OC_MAX_DIM) * 3;   // 1128
 constexpr int kMaxMapBytes = (OC_MAX_DIM + 2 * OC_PAD) * (OC_MAX_DIM + 2 * OC_PAD) * 3;          // 1728
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 4;   // default (and maximum) CTA size in warps; very large grids fall back to 2 or 1
 constexpr int kMaxTmplBytes = 8 * OC_MAX_CELLS * OC_OBS_CHANNELS;        // worst case: odd cell count -> 8 copies
 constexpr int kHdrFixed = 64 + 32;   // wall/blocked bitmaps, pot cells; then the scan list and the observation template
 
@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
     // cp.async (LDGSTS) of one tile's interior spans into span buffer `b`, 16 bytes per lane-op: env `el`'s slot is
     // filled from the 16-byte-aligned window that covers its span, so the span itself starts `mis` bytes into the
     // slot, with mis = (address of the span) mod 16.  The few over-read bytes belong to the env's own wall ring.
-    const long long tile_stride = (long long)gridDim.x * kWarpsPerCta;
+    const int cta_warps = (int)(blockDim.x >> 5), cta_threads = (int)blockDim.x;
+    const long long tile_stride = (long long)gridDim.x * cta_warps;
     auto prefetch_spans = [&](long long tl, int b) {
         const long long e0 = tl * epw;
         const int nv = (int)min((long long)epw, p.N - e0);
@@ -316,12 +317,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
     {
         if (p.tmpl_bytes) {
             const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
-            for (int i = tid; i < p.tmpl_chunks; i += kWarpsPerCta * 32) s_tmpl[i] = __ldg(tsrc + i);
+            for (int i = tid; i < p.tmpl_chunks; i += cta_threads) s_tmpl[i] = __ldg(tsrc + i);
         }
-        for (int i = tid; i < p.n_scan; i += kWarpsPerCta * 32) s_scan[i] = L->scan[i];
+        for (int i = tid; i < p.n_scan; i += cta_threads) s_scan[i] = L->scan[i];
         if (p.pf_invariant) {
             const int m0 = (int)((reinterpret_cast<uintptr_t>(p.st.maze_map) + (unsigned)p.span_off) & 15);
-            for (int f = tid; f < epw * p.nch; f += kWarpsPerCta * 32) {
+            for (int f = tid; f < epw * p.nch; f += cta_threads) {
                 const int el = (int)fastdiv((unsigned)f, p.magic_nch);
                 const int c = f - el * p.nch;
                 const int o = el * p.map_bytes;
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
     }
     __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    long long tile = (long long)blockIdx.x * kWarpsPerCta + warp;
+    long long tile = (long long)blockIdx.x * cta_warps + warp;
     int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // this lane's share of oc_step_extras.stats
     int buf = 0;
     Fields nf;
@@ -788,6 +789,7 @@ struct oc_layout {
     int epw;
     int smem_bytes;
     int warp_bytes;
+    int warps;                 // warps per CTA: 4 unless the layout's tiles are too big for shared memory
     int pf_bytes;
     int tmpl_smem_bytes;       // > 0: the static image (tmpl_k copies) is kept in shared memory
     unsigned char *tmpl_tile;
@@ -872,13 +874,13 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
         if (cudaFuncSetAttribute(oc_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oc_env_kernel<MODE>, kWarpsPerCta * 32, lay->smem_bytes) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oc_env_kernel<MODE>, lay->warps * 32, lay->smem_bytes) != cudaSuccess)
             return fail_cuda();
         lay->occ[MODE] = nb < 1 ? 1 : nb;
     }
     // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
     const long long resident = (long long)lay->num_sms * lay->occ[MODE];
-    const long long want = (kp.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long want = (kp.n_tiles + lay->warps - 1) / lay->warps;
     long long ctas = want;
     if (want > resident) {
         const long long k = (want + resident - 1) / resident;
@@ -888,7 +890,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3(kWarpsPerCta * 32);
+    cfg.blockDim = dim3((unsigned)lay->warps * 32);
     cfg.dynamicSmemBytes = (size_t)lay->smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1050,23 +1052,31 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + tmpl_smem;
     auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
-    int epw = 0;
-    for (int e = 16; e >= 2; e >>= 1)
-        if (size_ok(e) && kHdrBytesHost0 + pf_bytes_for(e) + kWarpsPerCta * warp_bytes_for(e) <= smem_cap / 8) { epw = e; break; }
-    if (!epw)
-        for (int e = 2; e <= 16; e <<= 1)
-            if (size_ok(e) && kHdrBytesHost0 + pf_bytes_for(e) + kWarpsPerCta * warp_bytes_for(e) <= smem_cap) { epw = e; break; }
+    // (warps per CTA, envs per warp): maximise the warps resident per SM -- limited by shared memory and by the 72
+    // registers x 896 threads the kernel is compiled for -- then prefer larger tiles, then larger CTAs
+    int epw = 0, W = kWarpsPerCta, best = 0;
+    for (int wv = kWarpsPerCta; wv >= 1; wv >>= 1)
+        for (int e = 16; e >= 2; e >>= 1) {
+            const int bytes = kHdrBytesHost0 + pf_bytes_for(e) + wv * warp_bytes_for(e);
+            if (!size_ok(e) || bytes > smem_cap) continue;
+            int ctas = smem_cap / (bytes + 1024);
+            if (ctas > 28 / wv) ctas = 28 / wv;
+            if (ctas < 1) ctas = 1;
+            const int score = ctas * wv;
+            if (score > best || (score == best && (e > epw || (e == epw && wv > W)))) { best = score; epw = e; W = wv; }
+        }
     if (const char *ev = std::getenv("OC_B200_EPW")) {
         const int v = std::atoi(ev);
         if ((v == 2 || v == 4 || v == 8 || v == 16) && size_ok(v) &&
-            kHdrBytesHost0 + pf_bytes_for(v) + kWarpsPerCta * warp_bytes_for(v) <= smem_cap) epw = v;
+            kHdrBytesHost0 + pf_bytes_for(v) + W * warp_bytes_for(v) <= smem_cap) epw = v;
     }
     if (!epw) { delete lay; return OC_ERR_UNSUPPORTED_LAYOUT; }
     lay->epw = epw;
     lay->warp_bytes = warp_bytes_for(epw);
     lay->pf_bytes = pf_bytes_for(epw);
     lay->tmpl_smem_bytes = tmpl_smem;
-    lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + kWarpsPerCta * lay->warp_bytes;
+    lay->warps = W;
+    lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + W * lay->warp_bytes;
     lay->num_sms = prop.multiProcessorCount;
     lay->occ[0] = lay->occ[1] = lay->occ[2] = 0;
     lay->device = device;
@@ -1102,7 +1112,7 @@ int oc_layout_query(const oc_layout *lay, oc_layout_info *info) {
     info->map_bytes_per_env = L.map_bytes;
     info->obs_bytes_per_agent = (int64_t)L.C * OC_OBS_CHANNELS;
     info->algorithmic_bytes = 58ll * L.C + 117;
-    info->envs_per_warp = lay->epw; info->warps_per_cta = kWarpsPerCta; info->smem_bytes_per_cta = lay->smem_bytes;
+    info->envs_per_warp = lay->epw; info->warps_per_cta = lay->warps; info->smem_bytes_per_cta = lay->smem_bytes;
     return OC_OK;
 }
 

@@ -442,3 +442,23 @@ def test_ct_rollout_manager_vdn_surface():
         assert_same(obs["__all__"].cpu().numpy(), np.concatenate([r0.reshape(B, -1), r1.reshape(B, -1)], 1), f"t={t} __all__")
         assert_same(rew["__all__"].cpu().numpy(), rr, f"t={t} reward __all__")
         assert_same(info["returned_episode_returns"].cpu().numpy(), rlog["returned_episode_returns"], f"t={t} returns")
+
+
+def _big_layout(h, w):
+    """Enclosed h x w kitchen with everything on the walls and a few interior counters (max-size stress)."""
+    rows = [["W"] * w for _ in range(h)]
+    for y in range(1, h - 1):
+        for x in range(1, w - 1):
+            rows[y][x] = " " if (x % 4 or y % 3) else "W"
+    rows[0][2], rows[0][w - 3] = "P", "P"
+    rows[h - 1][2], rows[h - 1][w - 3] = "O", "X"
+    rows[h // 2][0], rows[h // 2][w - 1] = "B", "O"
+    rows[1][1], rows[h - 2][w - 2] = "A", "A"
+    from jaxovercooked_b200.layouts import layout_grid_to_dict
+    return layout_grid_to_dict("\n".join("".join(r) for r in rows))
+
+
+@pytest.mark.parametrize("h,w", [(15, 15), (16, 16), (3, 16), (16, 3)])
+def test_maximum_grid_sizes(h, w):
+    """env_generator.py:220-223 allows up to 15x15; the ABI accepts up to 16x16."""
+    _rollout_compare(_big_layout(h, w), random_reset=True, max_steps=13, N=77, T=30, seed=h * w, every=2)
