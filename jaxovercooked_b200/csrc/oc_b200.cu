@@ -671,6 +671,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
                     (ai ? p.shaped1 : p.shaped0)[env] = (float)shaped;
                     if (p.ex.episode_returns) {   // wrappers/baselines.py:90-106, this lane = agent ai
                         const long long j = env * 2 + ai;
+                        // pin the four loaded trackers here: without this the compiler hoists their first use right
+                        // behind the loads and the warp stalls on DRAM before the observation phase
+                        asm volatile("" : "+f"(lw_er), "+f"(lw_el), "+f"(lw_rr), "+f"(lw_rl));
                         const float keep = done ? 0.f : 1.f, dn = done ? 1.f : 0.f;
                         const float nr = lw_er + (float)rew;
                         const float nl = lw_el + 1.f;
