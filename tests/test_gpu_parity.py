@@ -462,3 +462,27 @@ def _big_layout(h, w):
 def test_maximum_grid_sizes(h, w):
     """env_generator.py:220-223 allows up to 15x15; the ABI accepts up to 16x16."""
     _rollout_compare(_big_layout(h, w), random_reset=True, max_steps=13, N=77, T=30, seed=h * w, every=2)
+
+
+def test_unaligned_observation_buffers_take_the_plain_store_path():
+    """Observation pointers that are not 16-byte aligned cannot use the bulk-copy engine; results must not change."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    lay = ocb.overcooked_layouts["cramped_room"]
+    env = ocb.make("overcooked", layout=lay, random_reset=True, max_steps=6)
+    N = 100
+    _, st_a = env.reset(ocr.split(ocr.PRNGKey(0), N))
+    st_b = st_a.clone()
+    nbytes = N * 4 * 5 * 26
+    raw = torch.zeros(2 * nbytes + 64, dtype=torch.uint8, device="cuda")
+    o0 = raw[2:2 + nbytes].view(N, 4, 5, 26)                       # 2-byte aligned only
+    o1 = raw[nbytes + 22:2 * nbytes + 22].view(N, 4, 5, 26)
+    subs = ocr.split_chain(ocr.PRNGKey(1), 10)
+    for t in range(10):
+        a = {"agent_0": torch.randint(0, 6, (N,), dtype=torch.int32, device="cuda"),
+             "agent_1": torch.randint(0, 6, (N,), dtype=torch.int32, device="cuda")}
+        out = {"obs0": o0, "obs1": o1, "reward": torch.empty(N, device="cuda"), "shaped0": torch.empty(N, device="cuda"),
+               "shaped1": torch.empty(N, device="cuda"), "done": torch.empty(N, dtype=torch.bool, device="cuda")}
+        _, st_a, _, _, _ = env.step(ocr.LazySplit(subs[t], N), st_a, a, donate=True, out=out)
+        obs, st_b, *_ = env.step(ocr.LazySplit(subs[t], N), st_b, a, donate=True)
+        assert torch.equal(o0, obs["agent_0"]) and torch.equal(o1, obs["agent_1"])
