@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "liboc_b200.so")
+# OC_B200_LIB: alternative build of the same library (A/B tuning of kernel variants); never a different backend
+LIB_PATH = os.environ.get("OC_B200_LIB") or os.path.join(_PKG, "liboc_b200.so")
 
 OC_OK = 0
 PRNG_LEGACY = 0
