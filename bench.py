@@ -42,11 +42,11 @@ def parse():
     ap.add_argument("--layout", default="cramped_room")
     ap.add_argument("--padded-cl", action="store_true", help="use the 5x9-padded CL version of --layout")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
-    ap.add_argument("--rotate", type=int, default=4, help="independent env batches stepped round-robin")
+    ap.add_argument("--rotate", type=int, default=8, help="independent env batches stepped round-robin")
     ap.add_argument("--random-reset", action="store_true")
     ap.add_argument("--max-steps", type=int, default=400)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--e2e-steps", type=int, default=4000)
+    ap.add_argument("--e2e-steps", type=int, default=16000)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")

@@ -161,6 +161,19 @@ int oc_step_host(const oc_layout *layout, int64_t N, const uint32_t *keys, oc_st
                  const int32_t *h_actions, void *h_results, void *d_scratch, uint8_t *obs0, uint8_t *obs1,
                  const oc_step_extras *extras, void *stream);
 
+/* oc_step_host with every argument but the step's subkey and actions bound once (a closure over one env batch
+ * and one stream), so a host-side rollout loop pays one three-argument call per step:
+ *   create: `extras` must carry split_num / split_first (and optionally the LogWrapper / stats pointers);
+ *   step:   env i uses jax.random.split(*split_key, split_num)[split_first + i]; h_actions HOST i32[2,N];
+ *   wait:   blocks until the batch's stream has delivered the last step's results to h_results. */
+typedef struct oc_host_stepper oc_host_stepper;
+int  oc_host_stepper_create(const oc_layout *layout, int64_t N, oc_state state, void *h_results, void *d_scratch,
+                            uint8_t *obs0, uint8_t *obs1, const oc_step_extras *extras, void *stream,
+                            oc_host_stepper **out);
+int  oc_host_stepper_step(oc_host_stepper *stepper, const uint32_t *split_key, const int32_t *h_actions);
+int  oc_host_stepper_wait(oc_host_stepper *stepper);
+void oc_host_stepper_destroy(oc_host_stepper *stepper);
+
 /* env.get_obs under vmap: overcooked.py:250-364. */
 int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream);
 

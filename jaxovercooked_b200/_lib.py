@@ -48,7 +48,8 @@ class LayoutInfo(C.Structure):
 
 
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
-           "oc_reset", "oc_step", "oc_step_host", "oc_get_obs", "oc_prng_split", "oc_prng_chain")
+           "oc_reset", "oc_step", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
+           "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_prng_split", "oc_prng_chain")
 
 _lib = None
 
@@ -89,6 +90,15 @@ def load():
     lib.oc_step_host.restype = C.c_int
     lib.oc_step_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.POINTER(StepExtras), C.c_void_p]
+    lib.oc_host_stepper_create.restype = C.c_int
+    lib.oc_host_stepper_create.argtypes = [C.c_void_p, C.c_int64, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.POINTER(StepExtras), C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.oc_host_stepper_step.restype = C.c_int
+    lib.oc_host_stepper_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oc_host_stepper_wait.restype = C.c_int
+    lib.oc_host_stepper_wait.argtypes = [C.c_void_p]
+    lib.oc_host_stepper_destroy.restype = None
+    lib.oc_host_stepper_destroy.argtypes = [C.c_void_p]
     lib.oc_prng_split.restype = C.c_int
     lib.oc_prng_split.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.oc_prng_chain.restype = C.c_int

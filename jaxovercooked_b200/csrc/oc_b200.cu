@@ -1210,6 +1210,43 @@ int oc_step_host(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state
     return OC_OK;
 }
 
+struct oc_host_stepper {
+    const oc_layout *lay;
+    int64_t N;
+    oc_state state;
+    void *h_results, *d_scratch;
+    uint8_t *obs0, *obs1;
+    oc_step_extras extras;
+    void *stream;
+};
+
+int oc_host_stepper_create(const oc_layout *lay, int64_t N, oc_state state, void *h_results, void *d_scratch,
+                           uint8_t *obs0, uint8_t *obs1, const oc_step_extras *extras, void *stream,
+                           oc_host_stepper **out) {
+    if (!lay || !out || N <= 0 || !state_ok(state) || !h_results || !d_scratch || !obs0 || !obs1 || !extras)
+        return OC_ERR_INVALID_ARG;
+    oc_host_stepper *h = new (std::nothrow) oc_host_stepper();
+    if (!h) return OC_ERR_INVALID_ARG;
+    h->lay = lay; h->N = N; h->state = state; h->h_results = h_results; h->d_scratch = d_scratch;
+    h->obs0 = obs0; h->obs1 = obs1; h->extras = *extras; h->stream = stream;
+    *out = h;
+    return OC_OK;
+}
+
+int oc_host_stepper_step(oc_host_stepper *h, const uint32_t *split_key, const int32_t *h_actions) {
+    if (!h || !split_key || !h_actions) return OC_ERR_INVALID_ARG;
+    h->extras.split_key = split_key;
+    return oc_step_host(h->lay, h->N, nullptr, h->state, h_actions, h->h_results, h->d_scratch, h->obs0, h->obs1,
+                        &h->extras, h->stream);
+}
+
+int oc_host_stepper_wait(oc_host_stepper *h) {
+    if (!h) return OC_ERR_INVALID_ARG;
+    return cudaStreamSynchronize(static_cast<cudaStream_t>(h->stream)) == cudaSuccess ? OC_OK : fail_cuda();
+}
+
+void oc_host_stepper_destroy(oc_host_stepper *h) { delete h; }
+
 int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first, int64_t count, uint32_t *out,
                   void *stream_) {
     if (!key || !out || num < 1 || first < 0 || count < 0 || first + count > num || num > 0x7fffffffll)

@@ -340,28 +340,42 @@ class HostStepper:
         self.obs = {"agent_0": torch.empty((n, env.height, env.width, N_CHANNELS), dtype=torch.uint8, device=dev),
                     "agent_1": torch.empty((n, env.height, env.width, N_CHANNELS), dtype=torch.uint8, device=dev)}
         self._sp = env._state_ptrs(state, batch)
-        self._ex = _lib.StepExtras()
-        self._event = torch.cuda.Event()
-        self._fn = env._lib.oc_step_host
-        self._stream_ptr = C.c_void_p(self.stream.cuda_stream)
+        ex = _lib.StepExtras()
+        ex.split_num, ex.split_first = self.n_global, self.first
         self.stream.wait_stream(torch.cuda.current_stream(dev))
+        handle = C.c_void_p()
+        _lib.check(env._lib.oc_host_stepper_create(env._handle, n, env._state_ptrs(state, batch), self._results.data_ptr(),
+                                                   self._scratch.data_ptr(), self.obs["agent_0"].data_ptr(),
+                                                   self.obs["agent_1"].data_ptr(), C.byref(ex),
+                                                   C.c_void_p(self.stream.cuda_stream), C.byref(handle)),
+                   "oc_host_stepper_create")
+        self._h = handle
+        self._step, self._wait, self._destroy = (env._lib.oc_host_stepper_step, env._lib.oc_host_stepper_wait,
+                                                 env._lib.oc_host_stepper_destroy)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
     def step(self, key, actions=None):
         """Enqueue one step; `key` is the step's subkey (uint32[2] CUDA tensor), split per env inside the kernel.
         `actions`: a pinned int32[2,N] host tensor to use instead of `self.actions` (no host-side copy)."""
-        ex = self._ex
         act = self.actions if actions is None else actions
-        self._act_keepalive = act
-        ex.split_key, ex.split_num, ex.split_first = key.data_ptr(), self.n_global, self.first
-        self._key_keepalive = key
-        rc = self._fn(self.env._handle, self.n, None, self._sp, act.data_ptr(), self._results.data_ptr(),
-                      self._scratch.data_ptr(), self.obs["agent_0"].data_ptr(), self.obs["agent_1"].data_ptr(),
-                      C.byref(ex), self._stream_ptr)
-        _lib.check(rc, "oc_step_host")
-        self._event.record(self.stream)
+        self._keepalive = (key, act)
+        rc = self._step(self._h, key.data_ptr(), act.data_ptr())
+        if rc:
+            _lib.check(rc, "oc_host_stepper_step")
 
     def wait(self):
-        self._event.synchronize()
+        """Block until this batch's last enqueued step has delivered its results to the pinned host views."""
+        rc = self._wait(self._h)
+        if rc:
+            _lib.check(rc, "oc_host_stepper_wait")
 
 
 registered_envs = ["overcooked"]
