@@ -209,7 +209,7 @@ __device__ __forceinline__ Interact interact_cell(int obj, int status, int inv, 
 // ------------------------------------------------------------------------------------------------ kernel
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
     // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
@@ -346,7 +346,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
     __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
     asm volatile("griddepcontrol.wait;" ::: "memory");
     long long tile = (long long)blockIdx.x * cta_warps + warp;
-    int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // this lane's share of oc_step_extras.stats
     int buf = 0;
     Fields nf;
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
@@ -689,9 +688,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
                         p.ex.returned_episode[env * 2 + ai] = (uint8_t)done;
                     }
                 }
-                if (p.ex.stats && active) {
-                    if (ai == 0) { acc_done += done ? 1 : 0; acc_rew += rew; acc_s0 += shaped; acc_rr += st_rr; acc_rl += st_rl; }
-                    else acc_s1 += shaped;
+                if (p.ex.stats) {   // exact integer sums: warp-reduced per tile, one atomic per non-zero counter
+                    int v_done = (active && ai == 0 && done) ? 1 : 0;
+                    int v_rew = (active && ai == 0) ? rew : 0;
+                    int v_s0 = (active && ai == 0) ? shaped : 0;
+                    int v_s1 = (active && ai == 1) ? shaped : 0;
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        v_done += __shfl_xor_sync(0xffffffffu, v_done, o);
+                        v_rew += __shfl_xor_sync(0xffffffffu, v_rew, o);
+                        v_s0 += __shfl_xor_sync(0xffffffffu, v_s0, o);
+                        v_s1 += __shfl_xor_sync(0xffffffffu, v_s1, o);
+                        st_rr += __shfl_xor_sync(0xffffffffu, st_rr, o);
+                        st_rl += __shfl_xor_sync(0xffffffffu, st_rl, o);
+                    }
+                    if (lane == 0) {
+                        unsigned long long *sp = reinterpret_cast<unsigned long long *>(p.ex.stats);
+                        if (v_done) atomicAdd(sp + 0, (unsigned long long)v_done);
+                        if (v_rew) atomicAdd(sp + 1, (unsigned long long)v_rew);
+                        if (v_s0) atomicAdd(sp + 2, (unsigned long long)v_s0);
+                        if (v_s1) atomicAdd(sp + 3, (unsigned long long)v_s1);
+                        if (st_rr) atomicAdd(sp + 4, (unsigned long long)st_rr);
+                        if (st_rl) atomicAdd(sp + 5, (unsigned long long)st_rl);
+                    }
                 }
             }
         }
@@ -711,27 +730,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) oc_env_kernel(const __gr
         }
         __syncwarp();
     }
-    if (MODE == MODE_STEP && p.ex.stats) {   // exact integer sums: one atomic per warp and counter, only when non-zero
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc_done += __shfl_xor_sync(0xffffffffu, acc_done, o);
-            acc_rew += __shfl_xor_sync(0xffffffffu, acc_rew, o);
-            acc_s0 += __shfl_xor_sync(0xffffffffu, acc_s0, o);
-            acc_s1 += __shfl_xor_sync(0xffffffffu, acc_s1, o);
-            acc_rr += __shfl_xor_sync(0xffffffffu, acc_rr, o);
-            acc_rl += __shfl_xor_sync(0xffffffffu, acc_rl, o);
-        }
-        if (lane == 0) {
-            unsigned long long *sp = reinterpret_cast<unsigned long long *>(p.ex.stats);
-            if (acc_done) atomicAdd(sp + 0, (unsigned long long)acc_done);
-            if (acc_rew) atomicAdd(sp + 1, (unsigned long long)acc_rew);
-            if (acc_s0) atomicAdd(sp + 2, (unsigned long long)acc_s0);
-            if (acc_s1) atomicAdd(sp + 3, (unsigned long long)acc_s1);
-            if (acc_rr) atomicAdd(sp + 4, (unsigned long long)acc_rr);
-            if (acc_rl) atomicAdd(sp + 5, (unsigned long long)acc_rl);
-            if (blockIdx.x == 0 && warp == 0) atomicAdd(sp + 6, (unsigned long long)p.N);   // every env stepped once
-        }
-    }
+    if (MODE == MODE_STEP && p.ex.stats && blockIdx.x == 0 && tid == 0)   // every env stepped once
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.ex.stats) + 6, (unsigned long long)p.N);
     if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
@@ -1055,18 +1055,27 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + tmpl_smem;
     auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
-    // (warps per CTA, envs per warp): maximise the warps resident per SM -- limited by shared memory and by the 72
-    // registers x 896 threads the kernel is compiled for -- then prefer larger tiles, then larger CTAs
+    // (warps per CTA, envs per warp).  Resident warps per SM are limited by shared memory and by the 64 registers x
+    // 1024 threads the kernel is compiled for.  Measured on B200: beyond ~24 resident warps more warps stop paying,
+    // while larger tiles (full lanes in the step logic, fewer per-tile overheads) and 4-warp CTAs keep paying.  So:
+    // among the shapes that reach 24 resident warps take the largest tile, then the largest CTA; if none does,
+    // take the shape with the most resident warps.
     int epw = 0, W = kWarpsPerCta, best = 0;
+    bool best_enough = false;
     for (int wv = kWarpsPerCta; wv >= 1; wv >>= 1)
         for (int e = 16; e >= 2; e >>= 1) {
             const int bytes = kHdrBytesHost0 + pf_bytes_for(e) + wv * warp_bytes_for(e);
             if (!size_ok(e) || bytes > smem_cap) continue;
             int ctas = smem_cap / (bytes + 1024);
-            if (ctas > 28 / wv) ctas = 28 / wv;
+            if (ctas > 32 / wv) ctas = 32 / wv;
             if (ctas < 1) ctas = 1;
-            const int score = ctas * wv;
-            if (score > best || (score == best && (e > epw || (e == epw && wv > W)))) { best = score; epw = e; W = wv; }
+            const int warps = ctas * wv;
+            const bool enough = warps >= 24;
+            bool better;
+            if (enough != best_enough) better = enough;
+            else if (enough) better = e > epw || (e == epw && wv > W);
+            else better = warps > best || (warps == best && (e > epw || (e == epw && wv > W)));
+            if (!epw || better) { best = warps; best_enough = enough; epw = e; W = wv; }
         }
     if (const char *ev = std::getenv("OC_B200_EPW")) {
         const int v = std::atoi(ev);
