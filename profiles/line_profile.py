@@ -26,7 +26,7 @@ print("sass rows", len(data), "disasm instrs", len(lines))
 agg = collections.defaultdict(lambda: [0, 0])
 for r, ln in zip(data, lines):
     agg[ln][0] += int(r[iex] or 0); agg[ln][1] += int(r[isamp] or 0)
-src = open(sys.argv[5] if len(sys.argv) > 5 else "jaxovercooked_b200/csrc/oc_b200.cu").read().splitlines()
+src = open(sys.argv[5] if len(sys.argv) > 5 else "jaxovercooked_b200/csrc/oc_kernels.cuh").read().splitlines()
 tot = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 print("total warp-instr", tot, "samples", ts)
 for ln, (ex, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:ntop]:
