@@ -1,0 +1,148 @@
+// xla_ffi_shim.cc -- XLA FFI (typed custom call) handlers that forward XLA's device buffers to the C ABI of
+// liboc_b200.so (include/oc_b200.h).  This is the binding that lets the reference's own `Overcooked.reset / step /
+// get_obs` keep their signatures under jit / vmap / scan (see INTEGRATION.md section 1 and
+// jaxovercooked_b200/jax_ffi.py).
+//
+// STATUS: NOT BUILT AND NOT TESTED IN THIS IMAGE -- JAX (and with it xla/ffi/api/ffi.h) cannot be installed here.
+// __graft_entry__.build() compiles this file only when `import jax` succeeds:
+//   g++ -O2 -std=c++17 -shared -fPIC -I$(python -c "import jax; print(jax.ffi.include_dir())") -Iinclude
+//       -I/usr/local/cuda/include jaxovercooked_b200/csrc/xla_ffi_shim.cc -Ljaxovercooked_b200 -loc_b200
+//       -o jaxovercooked_b200/liboc_b200_ffi.so
+//
+// Conventions: the layout handle (an `oc_layout*` created once per env object with oc_layout_create) travels as an
+// int64 attribute -- the env is a static jit argument in the reference (baselines/IPPO_CL.py:454), so there is one
+// handle per compiled program.  N is the product of the leading (vmapped) dimensions of `keys`; the un-vmapped call
+// has N = 1.  The eleven State results are meant to be aliased onto the eleven State operands with
+// `input_output_aliases`, which makes oc_step run in place.
+#include <cstdint>
+#include <string>
+
+#include <cuda_runtime_api.h>
+
+#include "oc_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+namespace {
+
+template <typename T>
+int64_t leading_count(const T &keys) {   // keys: u32[..., 2]
+    int64_t n = 1;
+    const auto dims = keys.dimensions();
+    for (size_t i = 0; i + 1 < dims.size(); ++i) n *= dims[i];
+    return n;
+}
+
+ffi::Error to_error(int rc, const char *what) {
+    if (rc == OC_OK) return ffi::Error::Success();
+    return ffi::Error::Internal(std::string(what) + ": " + oc_status_string(rc));
+}
+
+#define OC_STATE_ARGS                                                                                             \
+    ffi::Buffer<ffi::U32> agent_pos, ffi::Buffer<ffi::S8> agent_dir, ffi::Buffer<ffi::S32> agent_dir_idx,         \
+        ffi::Buffer<ffi::S32> agent_inv, ffi::Buffer<ffi::U32> goal_pos, ffi::Buffer<ffi::U32> pot_pos,           \
+        ffi::Buffer<ffi::PRED> wall_map, ffi::Buffer<ffi::U8> maze_map, ffi::Buffer<ffi::S32> time,               \
+        ffi::Buffer<ffi::PRED> terminal, ffi::Buffer<ffi::S32> task_id
+#define OC_STATE_RETS                                                                                             \
+    ffi::ResultBuffer<ffi::U32> o_agent_pos, ffi::ResultBuffer<ffi::S8> o_agent_dir,                              \
+        ffi::ResultBuffer<ffi::S32> o_agent_dir_idx, ffi::ResultBuffer<ffi::S32> o_agent_inv,                     \
+        ffi::ResultBuffer<ffi::U32> o_goal_pos, ffi::ResultBuffer<ffi::U32> o_pot_pos,                            \
+        ffi::ResultBuffer<ffi::PRED> o_wall_map, ffi::ResultBuffer<ffi::U8> o_maze_map,                           \
+        ffi::ResultBuffer<ffi::S32> o_time, ffi::ResultBuffer<ffi::PRED> o_terminal,                              \
+        ffi::ResultBuffer<ffi::S32> o_task_id
+
+#define OC_IN_STATE                                                                                               \
+    oc_state {                                                                                                    \
+        agent_pos.typed_data(), agent_dir.typed_data(), agent_dir_idx.typed_data(), agent_inv.typed_data(),       \
+            goal_pos.typed_data(), pot_pos.typed_data(), reinterpret_cast<uint8_t *>(wall_map.typed_data()),      \
+            maze_map.typed_data(), time.typed_data(), reinterpret_cast<uint8_t *>(terminal.typed_data()),         \
+            task_id.typed_data()                                                                                  \
+    }
+#define OC_OUT_STATE                                                                                              \
+    oc_state {                                                                                                    \
+        o_agent_pos->typed_data(), o_agent_dir->typed_data(), o_agent_dir_idx->typed_data(),                      \
+            o_agent_inv->typed_data(), o_goal_pos->typed_data(), o_pot_pos->typed_data(),                         \
+            reinterpret_cast<uint8_t *>(o_wall_map->typed_data()), o_maze_map->typed_data(),                      \
+            o_time->typed_data(), reinterpret_cast<uint8_t *>(o_terminal->typed_data()), o_task_id->typed_data()  \
+    }
+
+// env.step under vmap  (jax_marl/environments/multi_agent_env.py:41-69)
+ffi::Error StepImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> keys, OC_STATE_ARGS,
+                    ffi::Buffer<ffi::S32> act0, ffi::Buffer<ffi::S32> act1, OC_STATE_RETS,
+                    ffi::ResultBuffer<ffi::U8> obs0, ffi::ResultBuffer<ffi::U8> obs1,
+                    ffi::ResultBuffer<ffi::F32> reward, ffi::ResultBuffer<ffi::F32> shaped0,
+                    ffi::ResultBuffer<ffi::F32> shaped1, ffi::ResultBuffer<ffi::PRED> done) {
+    const int64_t n = leading_count(keys);
+    const int rc = oc_step(reinterpret_cast<const oc_layout *>(layout), n, keys.typed_data(), OC_IN_STATE,
+                           act0.typed_data(), act1.typed_data(), /*reset_state=*/nullptr, OC_OUT_STATE,
+                           obs0->typed_data(), obs1->typed_data(), reward->typed_data(), shaped0->typed_data(),
+                           shaped1->typed_data(), reinterpret_cast<uint8_t *>(done->typed_data()),
+                           /*extras=*/nullptr, stream);
+    return to_error(rc, "oc_step");
+}
+
+// env.reset under vmap  (overcooked_environment/overcooked.py:136-248)
+ffi::Error ResetImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> keys, OC_STATE_RETS,
+                     ffi::ResultBuffer<ffi::U8> obs0, ffi::ResultBuffer<ffi::U8> obs1) {
+    const int64_t n = leading_count(keys);
+    const int rc = oc_reset(reinterpret_cast<const oc_layout *>(layout), n, keys.typed_data(), OC_OUT_STATE,
+                            obs0->typed_data(), obs1->typed_data(), stream);
+    return to_error(rc, "oc_reset");
+}
+
+// env.get_obs under vmap  (overcooked_environment/overcooked.py:250-364)
+ffi::Error GetObsImpl(cudaStream_t stream, int64_t layout, OC_STATE_ARGS, ffi::ResultBuffer<ffi::U8> obs0,
+                      ffi::ResultBuffer<ffi::U8> obs1) {
+    const int64_t n = time.element_count();
+    const int rc = oc_get_obs(reinterpret_cast<const oc_layout *>(layout), n, OC_IN_STATE, obs0->typed_data(),
+                              obs1->typed_data(), stream);
+    return to_error(rc, "oc_get_obs");
+}
+
+#define OC_BIND_STATE_ARGS()                                                                                      \
+    .Arg<ffi::Buffer<ffi::U32>>().Arg<ffi::Buffer<ffi::S8>>().Arg<ffi::Buffer<ffi::S32>>()                        \
+        .Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::U32>>().Arg<ffi::Buffer<ffi::U32>>()                   \
+        .Arg<ffi::Buffer<ffi::PRED>>().Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::S32>>()                   \
+        .Arg<ffi::Buffer<ffi::PRED>>().Arg<ffi::Buffer<ffi::S32>>()
+#define OC_BIND_STATE_RETS()                                                                                      \
+    .Ret<ffi::Buffer<ffi::U32>>().Ret<ffi::Buffer<ffi::S8>>().Ret<ffi::Buffer<ffi::S32>>()                        \
+        .Ret<ffi::Buffer<ffi::S32>>().Ret<ffi::Buffer<ffi::U32>>().Ret<ffi::Buffer<ffi::U32>>()                   \
+        .Ret<ffi::Buffer<ffi::PRED>>().Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::Buffer<ffi::S32>>()                   \
+        .Ret<ffi::Buffer<ffi::PRED>>().Ret<ffi::Buffer<ffi::S32>>()
+
+}  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcStep, StepImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("layout")
+                                  .Arg<ffi::Buffer<ffi::U32>>()   // keys
+                                  OC_BIND_STATE_ARGS()
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_0 actions
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_1 actions
+                                  OC_BIND_STATE_RETS()
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // obs agent_0
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // obs agent_1
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // reward
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_0
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_1
+                                  .Ret<ffi::Buffer<ffi::PRED>>()  // done
+);
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcReset, ResetImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("layout")
+                                  .Arg<ffi::Buffer<ffi::U32>>()   // keys
+                                  OC_BIND_STATE_RETS()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcGetObs, GetObsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("layout")
+                                  OC_BIND_STATE_ARGS()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
