@@ -189,6 +189,57 @@ int oc_prng_split(int prng_mode, const uint32_t *key, int64_t num, int64_t first
  * u32[2]) is advanced in place. */
 int oc_prng_chain(int prng_mode, uint32_t *key, int n, uint32_t *subkeys, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Actor-critic policy forward ("next" row f3 of the scope table): the consumer of the observations on the rollout
+ * path.  Replaces, for the flattened-observation MLP of architectures/mlp.py:11-59,
+ *     pi, value = network.apply(train_state.params, obs_batch)      baselines/IPPO_MLP.py:435
+ *     action    = pi.sample(seed=_rng)                               baselines/IPPO_MLP.py:438
+ *     log_prob  = pi.log_prob(action)                                baselines/IPPO_MLP.py:439
+ * with obs_batch = batchify(last_obs, env.agents, num_actors) (baselines/utils.py:48-61): uint8 rows, agent-major.
+ * FLOATING POINT: layer 1 is accumulated in fp32 from fp32 weights, layer 2 runs on the tensor cores with fp16
+ * operands and fp32 accumulation, tanh is the hardware approximation -- results are within a tolerance of the
+ * fp32 reference (tests/test_gpu_policy.py states it), never bit-exact. */
+
+#define OC_POLICY_HIDDEN 128         /* architectures/mlp.py:27,35,49,51 */
+#define OC_POLICY_MAX_ACTIONS 8
+
+typedef enum { OC_ACT_TANH = 0, OC_ACT_RELU = 1 } oc_activation;   /* architectures/mlp.py:20-23 */
+
+/* The six Dense layers in flax's creation order (Dense_0..2 actor, Dense_3..5 critic); kernels are [in, out]
+ * row-major float32, biases [out]; DEVICE pointers, read by oc_policy_create / oc_policy_update only. */
+typedef struct {
+    int32_t obs_dim;                 /* K = h * w * 26 (any even K >= 16 works) */
+    int32_t action_dim;              /* 1..OC_POLICY_MAX_ACTIONS (6 for Overcooked) */
+    int32_t activation;              /* oc_activation */
+    int32_t prng_mode;               /* oc_prng_mode, for the categorical draw */
+    const float *kernel[6];
+    const float *bias[6];
+    const uint8_t *obs_template;     /* HOST pointer, uint8[obs_dim], or NULL: an observation most rows are close to
+                                        (oc_layout_obs_template); layer 1 is evaluated as a correction to it.  Any
+                                        input is handled correctly with any template -- only the speed depends on it */
+} oc_policy_desc;
+
+typedef struct oc_policy oc_policy;  /* opaque: the parameters repacked for the kernels, in device memory */
+
+int oc_policy_create(const oc_policy_desc *desc, oc_policy **out);
+/* Re-read the parameters after an optimiser step (enqueue-only, same pointers or new ones). */
+int oc_policy_update(oc_policy *p, const oc_policy_desc *desc, void *stream);
+void oc_policy_destroy(oc_policy *p);
+
+/* logits[M, action_dim], value[M] for obs[M, obs_dim] (rows contiguous).  If `key` (DEVICE uint32[2]) is given,
+ * action[m] = argmax_a(logits[m, a] + gumbel(key, (1, M, A))[0, m, a]) and log_prob[m] = log_softmax(logits[m])[action[m]]
+ * are written too.  logits / value / action / log_prob may each be NULL. */
+int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *logits, float *value,
+                      const uint32_t *key, int32_t *action, float *log_prob, void *stream);
+
+/* The draw alone, for callers that keep `pi` around: action / log_prob (either may be NULL) from logits[M, A]. */
+int oc_policy_sample(int prng_mode, int64_t M, int32_t A, const float *logits, const uint32_t *key, int32_t *action,
+                     float *log_prob, void *stream);
+
+/* The layout's static observation (walls, piles, goals, pot locations: the part of get_obs that never changes),
+ * uint8[h * w * 26] into HOST memory: the natural `obs_template` for oc_policy_desc. */
+int oc_layout_obs_template(const oc_layout *layout, uint8_t *out);
+
 const char *oc_status_string(int status);
 int oc_version(void);
 

@@ -47,9 +47,16 @@ class LayoutInfo(C.Structure):
                 ("envs_per_warp", C.c_int32), ("warps_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32)]
 
 
+class PolicyDesc(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("activation", C.c_int32), ("prng_mode", C.c_int32),
+                ("kernel", C.c_void_p * 6), ("bias", C.c_void_p * 6), ("obs_template", C.c_void_p)]
+
+
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
            "oc_reset", "oc_step", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
-           "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_prng_split", "oc_prng_chain")
+           "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_prng_split", "oc_prng_chain",
+           "oc_policy_create", "oc_policy_update", "oc_policy_destroy", "oc_policy_forward", "oc_policy_sample",
+           "oc_layout_obs_template")
 
 _lib = None
 
@@ -103,6 +110,18 @@ def load():
     lib.oc_prng_split.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.oc_prng_chain.restype = C.c_int
     lib.oc_prng_chain.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oc_policy_create.restype = C.c_int
+    lib.oc_policy_create.argtypes = [C.POINTER(PolicyDesc), C.POINTER(C.c_void_p)]
+    lib.oc_policy_update.restype = C.c_int
+    lib.oc_policy_update.argtypes = [C.c_void_p, C.POINTER(PolicyDesc), C.c_void_p]
+    lib.oc_policy_destroy.restype = None
+    lib.oc_policy_destroy.argtypes = [C.c_void_p]
+    lib.oc_policy_forward.restype = C.c_int
+    lib.oc_policy_forward.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    lib.oc_policy_sample.restype = C.c_int
+    lib.oc_policy_sample.argtypes = [C.c_int, C.c_int64, C.c_int32] + [C.c_void_p] * 5
+    lib.oc_layout_obs_template.restype = C.c_int
+    lib.oc_layout_obs_template.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -384,6 +384,12 @@ int oc_layout_query(const oc_layout *lay, oc_layout_info *info) {
     return OC_OK;
 }
 
+int oc_layout_obs_template(const oc_layout *lay, uint8_t *out) {
+    if (!lay || !out) return OC_ERR_INVALID_ARG;
+    std::memcpy(out, lay->host.obs_tmpl, (size_t)lay->host.C * OC_OBS_CHANNELS);
+    return OC_OK;
+}
+
 int oc_reset(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state out, uint8_t *obs0, uint8_t *obs1,
              void *stream_) {
     if (!lay || N < 0 || !keys || !state_ok(out) || !obs0 || !obs1) return OC_ERR_INVALID_ARG;

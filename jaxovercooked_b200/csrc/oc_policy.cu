@@ -1,0 +1,608 @@
+// oc_policy.cu -- the actor-critic MLP forward of the rollout path (architectures/mlp.py:11-59 as called at
+// baselines/IPPO_MLP.py:435-439) for sm_100a: scope-table row f3, the consumer of the observation stream.
+//
+//   logits = Dense_2(act(Dense_1(act(Dense_0(x)))))          actor   K -> 128 -> 128 -> A
+//   value  = Dense_5(act(Dense_4(act(Dense_3(x)))))[:, 0]    critic  K -> 128 -> 128 -> 1
+//   x      = one uint8 observation row (h*w*26 bytes, > 95 % of them equal to the layout's static image)
+//
+// One persistent CTA per SM (16 warps) walks 128-row tiles:
+//   layer 1  (sparse, CUDA cores, fp32): each warp owns a row.  It XORs the row against the observation template
+//            in 16-byte pieces, turns the few differing bytes into (k, delta) entries in shared memory and
+//            accumulates base + sum(delta * W1[k, :]) with lane j holding hidden units 8j..8j+7 of the 256
+//            (actor | critic); `base` = bias + template . W1 is precomputed.  Any input is handled (a dense row just
+//            produces many entries); only the speed depends on how close rows are to the template.
+//   layer 2  (dense, tensor cores): the activated hidden tile is written as fp16 in the 128-byte-swizzled K-major
+//            layout tcgen05 reads; one thread issues 2 x 8 tcgen05.mma (M128 N128 K16, fp32 accumulators in TMEM
+//            columns 0..127 actor / 128..255 critic) against the resident fp16 W2 images, then tcgen05.commit.
+//   heads    all 16 warps read their TMEM quadrant / 64-column group with tcgen05.ld, apply bias + activation and
+//            the 128 -> A / 128 -> 1 heads on CUDA cores; 128 threads finish the row: logits, value and, when a key
+//            is given, the categorical draw (threefry gumbel, argmax) and its log-probability.
+//
+// Layer 1 is 1.5 kFMA per row when done sparsely against 133 kMAC densely; layer 2 has no sparsity, which is where
+// the tensor cores pay (DESIGN.md section 9 has the numbers).
+#include "oc_b200.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <new>
+
+#include "threefry.cuh"
+
+namespace {
+
+constexpr int kHid = OC_POLICY_HIDDEN;        // 128
+constexpr int kHid2 = 2 * kHid;               // actor | critic
+constexpr int kTileM = 128;
+constexpr int kPolWarps = 16;
+constexpr int kPolThreads = kPolWarps * 32;
+constexpr int kListCap = 512;                 // (k, delta) entries per warp between two flushes
+constexpr int kListWords = kListCap + 4;      // + padding to a multiple of 4 entries
+constexpr int kNetBytes = kTileM * kHid * 2;  // one fp16 128x128 operand image: 32 KB = 2 swizzle atoms of 16 KB
+constexpr int kTmemCols = 256;
+
+struct PolicySmall {
+    float base[kHid2];          // Dense_0/Dense_3 bias + template . kernel
+    float b2[kHid2];            // Dense_1 | Dense_4 bias
+    float hw[kHid * 8];         // Dense_2 kernel, row c = 8 floats (A used, rest 0)
+    float cw[kHid];             // Dense_5 kernel
+    float b3[8];                // Dense_2 bias (padded)
+    float b3c;                  // Dense_5 bias
+    float pad[3];
+};
+static_assert(sizeof(PolicySmall) % 16 == 0, "PolicySmall is copied in 16-byte pieces");
+
+// shared-memory carve-up (offsets from a 1024-byte aligned base)
+constexpr int kOffA = 0;
+constexpr int kOffW2 = kOffA + 2 * kNetBytes;
+constexpr int kOffSmall = kOffW2 + 2 * kNetBytes;
+constexpr int kOffHpA = kOffSmall + (int)sizeof(PolicySmall);
+constexpr int kOffHpC = kOffHpA + kTileM * 2 * 8 * 4;
+constexpr int kOffList = kOffHpC + kTileM * 2 * 4;
+constexpr int kOffMask = kOffList + kPolWarps * kListWords * 4;
+constexpr int kOffBar = kOffMask + 16 * 2 * 16;
+constexpr int kOffTmpl = kOffBar + 16;
+static_assert(kOffHpA % 16 == 0 && kOffList % 16 == 0 && kOffMask % 16 == 0 && kOffTmpl % 16 == 0, "alignment");
+
+struct PParams {
+    const float *w1;            // [K][256] fp32
+    const uint8_t *w2img;       // 2 x 32 KB fp16 images (swizzled, K-major, row = output unit)
+    const PolicySmall *small;
+    const uint8_t *tmpl;        // [K]
+    const uint4 *obs16;         // observation base rounded down to 16 bytes
+    int a0;                     // ... and the bytes that were rounded off
+    long long M;
+    int K, A, part;
+    int nvar, gshift, tv_stride;
+    int n_tiles;
+    float *logits, *value, *log_prob;
+    const uint32_t *key;
+    int32_t *action;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float act_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+    return ACT == OC_ACT_RELU ? fminf(fmaxf(x, 0.0f), 65504.0f) : act_tanh(x);
+}
+
+// mask with bit 7 of every non-zero byte set
+__device__ __forceinline__ uint32_t nz_bytes(uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
+
+// tcgen05 shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type=2 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), both K-major, N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kHid >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Categorical(logits).sample(seed=key) and .log_prob(action) for one row (distrax over jax.random.categorical):
+// action = argmax_a(logits[a] + gumbel(key, (1, M, A))[0, row, a]), first maximum wins; log_prob = log_softmax(logits)[action]
+__device__ __forceinline__ void sample_row(int part, uint32_t k0, uint32_t k1, int n, long long row, int A,
+                                           const float (&lg)[OC_POLICY_MAX_ACTIONS], int &arg, float &lp) {
+    float best = 0.f, mx = lg[0];
+    arg = 0;
+#pragma unroll
+    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a) {
+        if (a < A) {
+            // jax.random.gumbel: -log(-log(uniform(key, shape, minval=tiny, maxval=1)))
+            const uint32_t bits = bits_at(part, k0, k1, n, (int)(row * A + a));
+            const float f = __uint_as_float((bits >> 9) | 0x3f800000u) - 1.0f;
+            const float u = fmaxf(1.17549435e-38f, f + 1.17549435e-38f);
+            const float z = lg[a] - logf(-logf(u));
+            if (a == 0 || z > best) { best = z; arg = a; }
+            mx = fmaxf(mx, lg[a]);
+        }
+    }
+    float s = 0.f, la = 0.f;
+#pragma unroll
+    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
+        if (a < A) { s += expf(lg[a] - mx); if (a == arg) la = lg[a]; }
+    lp = la - (mx + logf(s));
+}
+
+__global__ void oc_policy_sample_kernel(int part, long long M, int A, const float *__restrict__ logits,
+                                        const uint32_t *__restrict__ key, int32_t *action, float *log_prob) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    float lg[OC_POLICY_MAX_ACTIONS];
+#pragma unroll
+    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a) lg[a] = a < A ? logits[row * A + a] : 0.f;
+    int arg;
+    float lp;
+    sample_row(part, __ldg(key), __ldg(key + 1), (int)(M * A), row, A, lg, arg, lp);
+    if (action) action[row] = arg;
+    if (log_prob) log_prob[row] = lp;
+}
+
+// accumulate `n` (k, delta) entries of this warp's list: acc[0..7] += delta * W1[k, 8*lane .. 8*lane+7]
+__device__ __forceinline__ void gather_rows(const float *__restrict__ w1, uint32_t *list, int n, int lane, float (&acc)[8]) {
+    if (lane < 3) list[n + lane] = 0u;       // pad to a multiple of 4 with (k=0, delta=0)
+    __syncwarp();
+    const float *wl = w1 + 8 * lane;
+    for (int i = 0; i < n; i += 4) {
+        const uint4 e4 = *reinterpret_cast<const uint4 *>(list + i);
+        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+        float4 wa[4], wb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 *wp = reinterpret_cast<const float4 *>(wl + (size_t)(e[u] >> 16) * kHid2);
+            wa[u] = __ldg(wp);
+            wb[u] = __ldg(wp + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float d = (float)(short)(e[u] & 0xffffu);
+            acc[0] = fmaf(d, wa[u].x, acc[0]); acc[1] = fmaf(d, wa[u].y, acc[1]);
+            acc[2] = fmaf(d, wa[u].z, acc[2]); acc[3] = fmaf(d, wa[u].w, acc[3]);
+            acc[4] = fmaf(d, wb[u].x, acc[4]); acc[5] = fmaf(d, wb[u].y, acc[5]);
+            acc[6] = fmaf(d, wb[u].z, acc[6]); acc[7] = fmaf(d, wb[u].w, acc[7]);
+        }
+    }
+    __syncwarp();
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = sm + kOffA;
+    uint8_t *sW2 = sm + kOffW2;
+    PolicySmall *sS = reinterpret_cast<PolicySmall *>(sm + kOffSmall);
+    float *hpA = reinterpret_cast<float *>(sm + kOffHpA);      // [128][2][8]
+    float *hpC = reinterpret_cast<float *>(sm + kOffHpC);      // [128][2]
+    uint32_t *lists = reinterpret_cast<uint32_t *>(sm + kOffList);
+    uint4 *masks = reinterpret_cast<uint4 *>(sm + kOffMask);   // [nvar][first, last]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + kOffBar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 8);
+    uint8_t *tmplv = sm + kOffTmpl;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.K;
+
+    // ---- one-time setup: resident W2 images, small parameters, template variants, TMEM, mbarrier
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.w2img);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW2);
+        for (int i = tid; i < 2 * kNetBytes / 16; i += kPolThreads) dst[i] = __ldg(src + i);
+        const uint4 *s2 = reinterpret_cast<const uint4 *>(p.small);
+        uint4 *d2 = reinterpret_cast<uint4 *>(sS);
+        for (int i = tid; i < (int)sizeof(PolicySmall) / 16; i += kPolThreads) d2[i] = __ldg(s2 + i);
+        const int g = 1 << p.gshift;
+        for (int i = tid; i < p.nvar * p.tv_stride; i += kPolThreads) {
+            const int v = i / p.tv_stride, j = i - v * p.tv_stride;
+            const int a = (p.a0 + v * g) & 15;
+            tmplv[i] = (j >= a && j < a + K) ? __ldg(p.tmpl + (j - a)) : (uint8_t)0;
+        }
+        uint8_t *mb = reinterpret_cast<uint8_t *>(masks);
+        for (int i = tid; i < p.nvar * 32; i += kPolThreads) {
+            const int v = i >> 5, j = i & 15, last = (i >> 4) & 1;
+            const int a = (p.a0 + v * g) & 15;
+            const int e = ((a + K - 1) & 15) + 1;
+            mb[i] = last ? (j < e ? 0xff : 0) : (j >= a ? 0xff : 0);
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_addr(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_addr(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // W2 image: generic-proxy writes -> tensor-core reads
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sA_u = smem_addr(sA), sW2_u = smem_addr(sW2), bar_u = smem_addr(mbar);
+    uint32_t phase = 0;
+    uint32_t *list = lists + warp * kListWords;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // ------------------------------------------------------------------ layer 1: one row per warp, 8 rounds
+        for (int rr = 0; rr < kTileM / kPolWarps; ++rr) {
+            const int row_l = rr * kPolWarps + warp;
+            const long long row = (long long)tile * kTileM + row_l;
+            float acc[8];
+            {
+                const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
+                const float4 b1 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane + 4);
+                acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+                acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+            }
+            if (row < p.M) {
+                const long long fo = row * K + p.a0;
+                const int a = (int)(fo & 15);
+                const int np = (a + K + 15) >> 4;
+                const int v = ((a - p.a0) & 15) >> p.gshift;
+                const uint4 *src = p.obs16 + (fo >> 4);
+                const uint8_t *tv = tmplv + v * p.tv_stride;
+                int n = 0;
+                for (int g0 = 0; g0 < np; g0 += 32) {
+                    const int q = g0 + lane;
+                    uint4 o = make_uint4(0, 0, 0, 0), t = o;
+                    if (q < np) {
+                        o = __ldg(src + q);
+                        t = *reinterpret_cast<const uint4 *>(tv + 16 * q);
+                    }
+                    uint4 x = make_uint4(o.x ^ t.x, o.y ^ t.y, o.z ^ t.z, o.w ^ t.w);
+                    if (q == 0) { const uint4 m = masks[2 * v]; x.x &= m.x; x.y &= m.y; x.z &= m.z; x.w &= m.w; }
+                    if (q == np - 1) { const uint4 m = masks[2 * v + 1]; x.x &= m.x; x.y &= m.y; x.z &= m.z; x.w &= m.w; }
+                    const uint32_t m0 = nz_bytes(x.x), m1 = nz_bytes(x.y), m2 = nz_bytes(x.z), m3 = nz_bytes(x.w);
+                    const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+                    if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
+                    int incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (n + total > kListCap) {          // a dense row: drain what is pending first
+                        gather_rows(p.w1, list, n, lane, acc);
+                        n = 0;
+                    }
+                    int pos = n + incl - cnt;
+                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, tw[4] = {t.x, t.y, t.z, t.w}, mw[4] = {m0, m1, m2, m3};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t mm = mw[i];
+                        while (mm) {
+                            const int sh = __ffs(mm) - 8;                 // bit 7 of byte b -> shift 8*b
+                            mm &= mm - 1;
+                            const int k = 16 * q + 4 * i + (sh >> 3) - a;
+                            const int dlt = (int)((ow[i] >> sh) & 255u) - (int)((tw[i] >> sh) & 255u);
+                            list[pos++] = ((uint32_t)k << 16) | ((uint32_t)dlt & 0xffffu);
+                        }
+                    }
+                    n += total;
+                    __syncwarp();
+                }
+                gather_rows(p.w1, list, n, lane, acc);
+            }
+            // activation, fp16, swizzled K-major store: lane -> net = lane >> 4, 16-byte chunk j = lane & 15 of the row
+            uint4 pk;
+            {
+                const __half2 h0 = __floats2half2_rn(activate<ACT>(acc[0]), activate<ACT>(acc[1]));
+                const __half2 h1 = __floats2half2_rn(activate<ACT>(acc[2]), activate<ACT>(acc[3]));
+                const __half2 h2 = __floats2half2_rn(activate<ACT>(acc[4]), activate<ACT>(acc[5]));
+                const __half2 h3 = __floats2half2_rn(activate<ACT>(acc[6]), activate<ACT>(acc[7]));
+                pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<const uint32_t *>(&h2); pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+            }
+            const int j = lane & 15;
+            uint8_t *dst = sA + (lane >> 4) * kNetBytes + (j >> 3) * (kNetBytes / 2) + row_l * 128 + (((j & 7) ^ (row_l & 7)) << 4);
+            *reinterpret_cast<uint4 *>(dst) = pk;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+
+        // ------------------------------------------------------------------ layer 2: 2 nets x 8 K-steps on the tensor cores
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int net = 0; net < 2; ++net) {
+#pragma unroll
+                for (int ks = 0; ks < kHid / 16; ++ks) {
+                    const uint32_t off = net * kNetBytes + (ks >> 2) * (kNetBytes / 2) + (ks & 3) * 32;
+                    umma_f16(tmem + net * kHid, umma_desc(sA_u + off), umma_desc(sW2_u + off), ks > 0 ? 1u : 0u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_u) : "memory");
+        }
+        {
+            uint32_t done = 0, spins = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}\n"
+                    : "=r"(done) : "r"(bar_u), "r"(phase) : "memory");
+                if (!done && ++spins > (1u << 26)) __trap();      // a lost MMA completion must not hang the GPU
+            }
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+        // ------------------------------------------------------------------ heads: TMEM quadrant (warp & 3), 64-column group (warp >> 2)
+        {
+            const int qd = warp & 3, grp = warp >> 2, net = grp >> 1, half = grp & 1;
+            const int row_l = 32 * qd + lane;
+            const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(net * kHid + half * 64);
+            if (net == 0) {
+                float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    float v[16];
+                    tmem_ld16(taddr + cc * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = half * 64 + cc * 16 + i;
+                        const float h = activate<ACT>(v[i] + sS->b2[c]);
+                        const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
+                        const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
+                        pa[0] = fmaf(h, wlo.x, pa[0]); pa[1] = fmaf(h, wlo.y, pa[1]);
+                        pa[2] = fmaf(h, wlo.z, pa[2]); pa[3] = fmaf(h, wlo.w, pa[3]);
+                        pa[4] = fmaf(h, whi.x, pa[4]); pa[5] = fmaf(h, whi.y, pa[5]);
+                        pa[6] = fmaf(h, whi.z, pa[6]); pa[7] = fmaf(h, whi.w, pa[7]);
+                    }
+                }
+                float4 *o = reinterpret_cast<float4 *>(hpA + (row_l * 2 + half) * 8);
+                o[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+                o[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
+            } else {
+                float pc = 0.f;
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    float v[16];
+                    tmem_ld16(taddr + cc * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = half * 64 + cc * 16 + i;
+                        pc = fmaf(activate<ACT>(v[i] + sS->b2[kHid + c]), sS->cw[c], pc);
+                    }
+                }
+                hpC[row_l * 2 + half] = pc;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+
+        // ------------------------------------------------------------------ finish the row: logits, value, categorical draw
+        if (tid < kTileM) {
+            const long long row = (long long)tile * kTileM + tid;
+            if (row < p.M) {
+                const int A = p.A;
+                float lg[OC_POLICY_MAX_ACTIONS];
+#pragma unroll
+                for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
+                    lg[a] = hpA[(tid * 2) * 8 + a] + hpA[(tid * 2 + 1) * 8 + a] + sS->b3[a];
+                if (p.logits) {
+#pragma unroll
+                    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
+                        if (a < A) p.logits[row * A + a] = lg[a];
+                }
+                if (p.value) p.value[row] = hpC[tid * 2] + hpC[tid * 2 + 1] + sS->b3c;
+                if (p.key) {
+                    int arg;
+                    float lp;
+                    sample_row(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(p.M * A), row, A, lg, arg, lp);
+                    if (p.action) p.action[row] = arg;
+                    if (p.log_prob) p.log_prob[row] = lp;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// Repack the reference's parameter pytree for the kernel above.
+struct PackArgs {
+    const float *kernel[6];
+    const float *bias[6];
+    const uint8_t *tmpl;
+    float *w1;
+    uint8_t *w2img;
+    PolicySmall *small;
+    int K, A;
+};
+
+__global__ void oc_policy_pack_kernel(const PackArgs a) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    // layer 1: [K][actor 128 | critic 128]
+    for (long long i = gtid; i < (long long)a.K * kHid2; i += gstride) {
+        const int k = (int)(i / kHid2), j = (int)(i % kHid2);
+        a.w1[i] = j < kHid ? a.kernel[0][(size_t)k * kHid + j] : a.kernel[3][(size_t)k * kHid + (j - kHid)];
+    }
+    // layer 2: B[n][k] = kernel[k][n] as fp16 in the swizzled K-major image
+    __half *img = reinterpret_cast<__half *>(a.w2img);
+    for (long long i = gtid; i < 2ll * kHid * kHid; i += gstride) {
+        const int net = (int)(i / (kHid * kHid)), r = (int)(i % (kHid * kHid));
+        const int n = r / kHid, k = r % kHid;
+        const float w = a.kernel[net ? 4 : 1][(size_t)k * kHid + n];
+        const int off = net * kNetBytes + (k >> 6) * (kNetBytes / 2) + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+        img[off >> 1] = __float2half_rn(w);
+    }
+    if (blockIdx.x == 0) {
+        for (int j = threadIdx.x; j < kHid2; j += blockDim.x) {
+            const float *kern = j < kHid ? a.kernel[0] : a.kernel[3];
+            const int jj = j < kHid ? j : j - kHid;
+            float s = (j < kHid ? a.bias[0] : a.bias[3])[jj];
+            for (int k = 0; k < a.K; ++k) {
+                const int t = a.tmpl[k];
+                if (t) s = fmaf((float)t, kern[(size_t)k * kHid + jj], s);
+            }
+            a.small->base[j] = s;
+            a.small->b2[j] = (j < kHid ? a.bias[1] : a.bias[4])[jj];
+        }
+        for (int i = threadIdx.x; i < kHid * 8; i += blockDim.x) {
+            const int c = i >> 3, q = i & 7;
+            a.small->hw[i] = q < a.A ? a.kernel[2][(size_t)c * a.A + q] : 0.f;
+        }
+        for (int c = threadIdx.x; c < kHid; c += blockDim.x) a.small->cw[c] = a.kernel[5][c];
+        if (threadIdx.x < 8) a.small->b3[threadIdx.x] = threadIdx.x < a.A ? a.bias[2][threadIdx.x] : 0.f;
+        if (threadIdx.x == 0) { a.small->b3c = a.bias[5][0]; a.small->pad[0] = a.small->pad[1] = a.small->pad[2] = 0.f; }
+    }
+}
+
+int gcd16(int k) {
+    int g = 16;
+    while (k % g) g >>= 1;
+    return g;
+}
+
+}  // namespace
+
+struct oc_policy {
+    int K, A, act, part;
+    int nvar, gshift, tv_stride;
+    int num_sms;
+    size_t smem_bytes;
+    float *w1;
+    uint8_t *w2img;
+    PolicySmall *small;
+    uint8_t *tmpl;
+};
+
+extern "C" {
+
+static int policy_pack(oc_policy *p, const oc_policy_desc *d, cudaStream_t stream) {
+    PackArgs a;
+    for (int i = 0; i < 6; ++i) {
+        if (!d->kernel[i] || !d->bias[i]) return OC_ERR_INVALID_ARG;
+        a.kernel[i] = d->kernel[i];
+        a.bias[i] = d->bias[i];
+    }
+    a.tmpl = p->tmpl; a.w1 = p->w1; a.w2img = p->w2img; a.small = p->small; a.K = p->K; a.A = p->A;
+    oc_policy_pack_kernel<<<p->num_sms * 2, 256, 0, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+}
+
+void oc_policy_destroy(oc_policy *p) {
+    if (!p) return;
+    cudaFree(p->w1); cudaFree(p->w2img); cudaFree(p->small); cudaFree(p->tmpl);
+    delete p;
+}
+
+int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
+    if (!d || !out) return OC_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (d->obs_dim < 32 || d->obs_dim > 65535 || d->action_dim < 1 || d->action_dim > OC_POLICY_MAX_ACTIONS ||
+        (d->activation != OC_ACT_TANH && d->activation != OC_ACT_RELU) ||
+        (d->prng_mode != OC_PRNG_THREEFRY_LEGACY && d->prng_mode != OC_PRNG_THREEFRY_PARTITIONABLE))
+        return OC_ERR_INVALID_ARG;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return OC_ERR_NO_DEVICE;
+    if (prop.major != 10) return OC_ERR_NO_DEVICE;
+    oc_policy *p = new (std::nothrow) oc_policy();
+    if (!p) return OC_ERR_INVALID_ARG;
+    p->K = d->obs_dim; p->A = d->action_dim; p->act = d->activation; p->part = d->prng_mode;
+    p->num_sms = prop.multiProcessorCount;
+    const int g = gcd16(p->K);
+    p->gshift = g == 16 ? 4 : g == 8 ? 3 : g == 4 ? 2 : g == 2 ? 1 : 0;
+    p->nvar = 16 / g;
+    p->tv_stride = ((p->K + 30) / 16) * 16;
+    p->smem_bytes = (size_t)kOffTmpl + (size_t)p->nvar * p->tv_stride + 1024;
+    if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return OC_ERR_UNSUPPORTED_LAYOUT; }
+    if (cudaMalloc(&p->w1, (size_t)p->K * kHid2 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->w2img, 2 * kNetBytes) != cudaSuccess || cudaMalloc(&p->small, sizeof(PolicySmall)) != cudaSuccess ||
+        cudaMalloc(&p->tmpl, p->K) != cudaSuccess) {
+        oc_policy_destroy(p);
+        return OC_ERR_CUDA;
+    }
+    cudaError_t e = d->obs_template ? cudaMemcpy(p->tmpl, d->obs_template, p->K, cudaMemcpyHostToDevice)
+                                    : cudaMemset(p->tmpl, 0, p->K);
+    if (e != cudaSuccess ||
+        cudaFuncSetAttribute(oc_policy_kernel<OC_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(oc_policy_kernel<OC_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
+        oc_policy_destroy(p);
+        return OC_ERR_CUDA;
+    }
+    const int rc = policy_pack(p, d, nullptr);
+    if (rc != OC_OK || cudaStreamSynchronize(nullptr) != cudaSuccess) {
+        oc_policy_destroy(p);
+        return rc != OC_OK ? rc : OC_ERR_CUDA;
+    }
+    *out = p;
+    return OC_OK;
+}
+
+int oc_policy_update(oc_policy *p, const oc_policy_desc *d, void *stream) {
+    if (!p || !d || d->obs_dim != p->K || d->action_dim != p->A) return OC_ERR_INVALID_ARG;
+    return policy_pack(p, d, static_cast<cudaStream_t>(stream));
+}
+
+int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *logits, float *value,
+                      const uint32_t *key, int32_t *action, float *log_prob, void *stream_) {
+    if (!p || M < 0 || !obs) return OC_ERR_INVALID_ARG;
+    if ((action || log_prob) && !key) return OC_ERR_INVALID_ARG;
+    if (M == 0) return OC_OK;
+    if (M * p->A > 0x7fffffffll) return OC_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(key) |
+         reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(log_prob)) & 3u)
+        return OC_ERR_ALIGNMENT;
+    PParams k;
+    std::memset(&k, 0, sizeof(k));
+    k.w1 = p->w1; k.w2img = p->w2img; k.small = p->small; k.tmpl = p->tmpl;
+    const uintptr_t ob = reinterpret_cast<uintptr_t>(obs);
+    k.a0 = (int)(ob & 15u);
+    k.obs16 = reinterpret_cast<const uint4 *>(ob - (uintptr_t)k.a0);
+    k.M = M; k.K = p->K; k.A = p->A; k.part = p->part;
+    k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
+    k.n_tiles = (int)((M + kTileM - 1) / kTileM);
+    k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
+    const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (p->act == OC_ACT_RELU) oc_policy_kernel<OC_ACT_RELU><<<grid, kPolThreads, p->smem_bytes, stream>>>(k);
+    else oc_policy_kernel<OC_ACT_TANH><<<grid, kPolThreads, p->smem_bytes, stream>>>(k);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+}
+
+int oc_policy_sample(int prng_mode, int64_t M, int32_t A, const float *logits, const uint32_t *key, int32_t *action,
+                     float *log_prob, void *stream) {
+    if (M < 0 || A < 1 || A > OC_POLICY_MAX_ACTIONS || !logits || !key ||
+        (prng_mode != OC_PRNG_THREEFRY_LEGACY && prng_mode != OC_PRNG_THREEFRY_PARTITIONABLE) || M * A > 0x7fffffffll)
+        return OC_ERR_INVALID_ARG;
+    if (M == 0) return OC_OK;
+    oc_policy_sample_kernel<<<(unsigned)((M + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        prng_mode, M, A, logits, key, action, log_prob);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+}
+
+}  // extern "C"

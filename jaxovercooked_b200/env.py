@@ -290,6 +290,14 @@ class Overcooked:
         return a.contiguous()
 
     # ------------------------------------------------------------------ metadata the callers read
+    def obs_template(self):
+        """The layout's static observation (uint8 numpy [h, w, 26]): what `get_obs` returns minus everything that can
+        change.  `policy.ActorCritic.bind(..., obs_template=env.obs_template())` evaluates layer 1 relative to it."""
+        import numpy as np
+        out = np.empty((self.height, self.width, 26), np.uint8)
+        _lib.check(self._lib.oc_layout_obs_template(self._handle, out.ctypes.data), "oc_layout_obs_template")
+        return out
+
     def is_terminal(self, state):
         return (state.time >= self.max_steps) | state.terminal                 # overcooked.py:644-647
 

@@ -190,6 +190,54 @@ def _r_choice(key, a, shape=(), replace=True, p=None, axis=0):
 
 # ---------------------------------------------------------------------------------------------- install
 
+class _LinenModule:
+    """flax.linen.Module stand-in: annotated class attributes become constructor fields; `apply(variables, x)`
+    runs `__call__` with the submodules drawing their parameters from variables["params"] in creation order
+    (`Dense_0`, `Dense_1`, ... -- flax's auto-naming for unnamed submodules inside an `nn.compact` method)."""
+    _ctx = None
+
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
+        fields = list(getattr(cls, "__annotations__", {}))
+
+        def __init__(self, *a, **k):
+            for name, val in zip(fields, a):
+                setattr(self, name, val)
+            for name in fields[len(a):]:
+                setattr(self, name, k[name] if name in k else getattr(cls, name))
+        cls.__init__ = __init__
+
+    def apply(self, variables, *args):
+        prev = _LinenModule._ctx
+        _LinenModule._ctx = {"params": variables["params"], "count": {}}
+        try:
+            return self(*args)
+        finally:
+            _LinenModule._ctx = prev
+
+
+class _LinenDense:
+    def __init__(self, features, kernel_init=None, bias_init=None, use_bias=True, **_):
+        self.features, self.use_bias = features, use_bias
+
+    def __call__(self, x):
+        ctx = _LinenModule._ctx
+        i = ctx["count"].get("Dense", 0)
+        ctx["count"]["Dense"] = i + 1
+        p = ctx["params"]["Dense_%d" % i]
+        kernel = np.asarray(p["kernel"], dtype=np.float32)
+        assert kernel.shape[1] == self.features, (kernel.shape, self.features)
+        y = np.asarray(x, dtype=np.float32) @ kernel          # promote_dtype(inputs, kernel): uint8 obs -> float32
+        if self.use_bias:
+            y = y + np.asarray(p["bias"], dtype=np.float32)
+        return _wrap(y.astype(np.float32))
+
+
+class _Categorical:
+    def __init__(self, logits=None, probs=None):
+        self.logits = logits
+
+
 def install(partitionable=False):
     """Register the stand-in modules. Idempotent."""
     _Cfg.partitionable = bool(partitionable)
@@ -267,7 +315,24 @@ def install(partitionable=False):
     saff = types.ModuleType("safetensors.flax")
     saff.save_file = saff.load_file = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
 
+    # flax.linen / distrax: just enough to execute architectures/mlp.py (ActorCritic.__call__) unmodified
+    linen = types.ModuleType("flax.linen")
+    linen.__path__ = []
+    linen.Module = _LinenModule
+    linen.Dense = _LinenDense
+    linen.compact = lambda f: f
+    linen.relu = lambda x: _wrap(np.maximum(np.asarray(x), np.float32(0)))
+    linen.tanh = lambda x: _wrap(np.tanh(np.asarray(x, dtype=np.float32)))
+    inits = types.ModuleType("flax.linen.initializers")
+    inits.constant = lambda v: ("constant", v)
+    inits.orthogonal = lambda scale=1.0: ("orthogonal", scale)
+    linen.initializers = inits
+    flax.linen = linen
+    distrax = types.ModuleType("distrax")
+    distrax.Categorical = _Categorical
+
     sys.modules.update({
+        "flax.linen": linen, "flax.linen.initializers": inits, "distrax": distrax,
         "jax": jax, "jax.numpy": jnp, "jax.lax": lax, "jax.random": rnd, "jax.tree": tree,
         "chex": chex, "flax": flax, "flax.struct": struct, "flax.core": core,
         "flax.core.frozen_dict": fd, "flax.traverse_util": trav,
@@ -323,4 +388,5 @@ def load_reference(ref_root="/root/reference", partitionable=False):
     ns.common = oe.common
     ns.LogWrapper = wb.LogWrapper
     ns.FrozenDict = sys.modules["flax.core.frozen_dict"].FrozenDict
+    ns.ActorCritic = _load("architectures.mlp", "architectures/mlp.py").ActorCritic
     return ns

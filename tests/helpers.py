@@ -12,7 +12,13 @@ LOG_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns", 
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Environment trajectories (P_* are the actor-critic fixtures, see policy_cases)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if not n.startswith("P_")]
+
+
+def policy_cases():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "P_*.npz")))
 
 
 def load_golden(case):

@@ -1,0 +1,159 @@
+"""-m gpu: the sm_100a actor-critic forward (oc_policy_*) against the float32 oracle and the reference-derived fixtures.
+
+TOLERANCE (floating point, stated here as the task requires): layer 1 is fp32, layer 2 multiplies fp16 operands with
+fp32 accumulation on the tensor cores, tanh is `tanh.approx.f32` (|err| <= 2^-10.99).  With the reference's initialiser
+scales the logits head has column norm 0.01 and the value head 1.0, so the bound is relative to the size of the output:
+    |got - ref| <= TOL * max(1, max|ref|) * head_scale        TOL = 1e-2, head_scale = 0.01 (logits) | 1.0 (value)
+The measured maxima on the fixtures are about a fifth of that (printed by the test with -s).
+"""
+import numpy as np
+import pytest
+import torch
+
+import jaxovercooked_b200 as ocb
+from jaxovercooked_b200 import random as jr
+from jaxovercooked_b200.policy import ActorCritic
+from oracle import policy_oracle as po
+from oracle import prng
+from tests.gpu_helpers import keys_to_dev
+from tests.helpers import policy_cases
+from tests.test_policy_oracle import load_policy_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def check_outputs(logits, value, ref_logits, ref_value, what):
+    el = np.abs(logits - ref_logits).max() / (0.01 * max(1.0, np.abs(ref_logits).max() / 0.01))
+    ev = np.abs(value - ref_value).max() / max(1.0, np.abs(ref_value).max())
+    print(f"{what}: scaled max error logits {el:.2e} value {ev:.2e}")
+    assert np.isfinite(logits).all() and np.isfinite(value).all(), what
+    assert el <= TOL, f"{what}: logits off by {el:.3e} (scaled)"
+    assert ev <= TOL, f"{what}: value off by {ev:.3e} (scaled)"
+
+
+def template_for(case):
+    if case == "P_cramped_room":
+        return ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"]).obs_template()
+    if case == "P_padded_5x9":
+        return ocb.make("overcooked", layout=ocb.cl_sequence_padded()["coord_ring"]).obs_template()
+    return None
+
+
+@pytest.mark.parametrize("case", policy_cases())
+@pytest.mark.parametrize("act", ["tanh", "relu"])
+@pytest.mark.parametrize("use_template", [False, True])
+def test_forward_matches_reference_fixture(case, act, use_template):
+    g, meta, params = load_policy_case(case)
+    tmpl = template_for(case) if use_template else None
+    if use_template and tmpl is None:
+        tmpl = g["obs"][0]                       # any row works as a template: only the speed depends on it
+    net = ActorCritic(meta["action_dim"], activation=act)
+    P = net.params_from_numpy(params)
+    net.bind(P, obs_template=tmpl)
+    obs = torch.from_numpy(g["obs"]).cuda()
+    pi, value = net.apply(P, obs)
+    check_outputs(pi.logits.cpu().numpy(), value.cpu().numpy(), g["logits_" + act], g["value_" + act], f"{case}/{act}")
+
+
+@pytest.mark.parametrize("M", [1, 2, 127, 128, 129, 1000])
+@pytest.mark.parametrize("K,offset", [(520, 0), (520, 8), (1170, 0), (1170, 2), (1170, 6), (208, 0), (2600, 0), (546, 3)])
+def test_row_counts_and_alignments(M, K, offset):
+    """Tail tiles, single rows and observation buffers at every alignment the byte stream can have."""
+    rng = np.random.default_rng(M * 7919 + K + offset)
+    params = po.make_params(K, K)
+    tmpl = (rng.integers(0, 2, K) * (rng.random(K) < 0.05)).astype(np.uint8)
+    obs = np.tile(tmpl, (M, 1))
+    flips = rng.random((M, K)) < 0.02
+    obs[flips] = rng.integers(0, 21, flips.sum()).astype(np.uint8)
+    buf = torch.zeros(M * K + 64, dtype=torch.uint8, device="cuda")
+    view = buf[offset:offset + M * K].view(M, K)
+    view.copy_(torch.from_numpy(obs))
+    net = ActorCritic(6)
+    P = net.params_from_numpy(params)
+    net.bind(P, obs_template=tmpl)
+    pi, value = net.apply(P, view)
+    lo, vo = po.forward(params, obs)
+    check_outputs(pi.logits.cpu().numpy(), value.cpu().numpy(), lo, vo, f"M={M} K={K} off={offset}")
+
+
+@pytest.mark.parametrize("impl", ["threefry_legacy", "threefry_partitionable"])
+def test_fused_sampling(impl):
+    part = impl == "threefry_partitionable"
+    g, meta, params = load_policy_case("P_cramped_room")
+    net = ActorCritic(6, prng_impl=impl)
+    P = net.params_from_numpy(params)
+    obs = torch.from_numpy(g["obs"]).cuda()
+    key_np = prng.PRNGKey(1234)
+    key = keys_to_dev(key_np)
+    action, log_prob, value, logits = net.act(P, obs, key, want_logits=True)
+    logits_np = logits.cpu().numpy()
+    a_ref, z = po.sample(key_np, logits_np, part)
+    top2 = np.sort(z, axis=-1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5              # logf differs by <= 1 ulp between libm and the device
+    a = action.cpu().numpy()
+    assert a.dtype == np.int32
+    np.testing.assert_array_equal(a[clear], a_ref[clear])
+    assert clear.mean() > 0.99
+    np.testing.assert_allclose(log_prob.cpu().numpy(), po.log_prob(logits_np, a), atol=2e-6)
+    # the split calls of the reference (apply, then pi.sample, then pi.log_prob) give the same numbers
+    pi, value2 = net.apply(P, obs)
+    torch.testing.assert_close(pi.logits, logits, rtol=0, atol=0)
+    torch.testing.assert_close(value2, value, rtol=0, atol=0)
+    torch.testing.assert_close(pi.sample(seed=key), action, rtol=0, atol=0)
+    torch.testing.assert_close(pi.log_prob(action), log_prob, rtol=0, atol=2e-6)
+
+
+def test_parameter_update_is_picked_up():
+    g, meta, params = load_policy_case("P_cramped_room")
+    net = ActorCritic(6)
+    P = net.params_from_numpy(params)
+    obs = torch.from_numpy(g["obs"]).cuda()
+    _, v0 = net.apply(P, obs)
+    with torch.no_grad():
+        P["params"]["Dense_5"]["bias"].add_(1.5)
+        P["params"]["Dense_3"]["kernel"].mul_(0.5)
+    _, v1 = net.apply(P, obs)
+    params["params"]["Dense_5"]["bias"] = params["params"]["Dense_5"]["bias"] + np.float32(1.5)
+    params["params"]["Dense_3"]["kernel"] = params["params"]["Dense_3"]["kernel"] * np.float32(0.5)
+    lo, vo = po.forward(params, g["obs"])
+    assert np.abs(v1.cpu().numpy() - vo).max() <= TOL * max(1.0, np.abs(vo).max())
+    assert (v1 - v0).abs().max() > 0.5
+
+
+def test_rollout_loop_env_and_policy():
+    """obs -> act -> env.step for 24 steps: the policy sees what the env kernel wrote (rollout-buffer rows, agent-major)."""
+    n, T = 300, 24
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"])
+    net = ActorCritic(env.action_space().n)
+    params = po.make_params(5, 520)
+    # a head that is not tiny, so that the actions depend on the observation
+    params["params"]["Dense_2"]["kernel"] = (params["params"]["Dense_2"]["kernel"] * np.float32(300)).astype(np.float32)
+    P = net.params_from_numpy(params)
+    net.bind(P, obs_template=env.obs_template())
+    rng = jr.PRNGKey(30)
+    rng, sub = jr.split(rng)
+    obs, state = env.reset(jr.split(sub, n))
+    for t in range(T):
+        rng, k_act, k_step = jr.split(rng, 3)
+        batch = torch.cat([obs["agent_0"].reshape(n, -1), obs["agent_1"].reshape(n, -1)], dim=0)      # batchify
+        action, log_prob, value, logits = net.act(P, batch, k_act, want_logits=True)
+        lo, vo = po.forward(params, batch.cpu().numpy())
+        check_outputs(logits.cpu().numpy(), value.cpu().numpy(), lo, vo, f"step {t}")
+        acts = {"agent_0": action[:n], "agent_1": action[n:]}
+        obs, state, reward, done, info = env.step(jr.split(k_step, n), state, acts)
+    assert int(state.time.max()) == T
+
+
+def test_errors():
+    net = ActorCritic(6)
+    params = po.make_params(1, 520)
+    P = net.params_from_numpy(params)
+    with pytest.raises(ValueError):
+        net.apply(P, torch.zeros((4, 520), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        net.bind(P, obs_template=np.zeros(100, np.uint8))
+    bad = {"params": dict(P["params"])}
+    bad["params"]["Dense_1"] = {"kernel": torch.zeros((128, 64), device="cuda"), "bias": torch.zeros(64, device="cuda")}
+    with pytest.raises(ValueError):
+        net.apply(bad, torch.zeros((4, 520), dtype=torch.uint8, device="cuda"))
