@@ -50,6 +50,11 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
+    ap.add_argument("--policy-input", default="cells", choices=["cells", "obs"],
+                    help="with --policy: read the env kernel's compact observations (default) or scan the uint8 observations")
+    ap.add_argument("--policy", action="store_true",
+                    help="scope row f3: actions come from the actor-critic MLP (oc_policy_forward on the previous "
+                         "observations) instead of the uniform stand-in; reports the whole rollout step")
     return ap.parse_args()
 
 
@@ -257,12 +262,30 @@ def run_ours(args):
         rngs.append(ks[0].clone())
         _, st = wenv.reset(ocr.split(ks[1], n_global, first=first, count=N))
         states.append(st)
-    outs = [{"obs0": torch.empty((N, h, w, 26), dtype=torch.uint8, device=dev),
-             "obs1": torch.empty((N, h, w, 26), dtype=torch.uint8, device=dev),
+    obs_all = [torch.empty((2 * N, h * w * 26), dtype=torch.uint8, device=dev) for _ in range(OBS_SLOTS)]   # agent-major rows
+    outs = [{"obs0": obs_all[i][:N].view(N, h, w, 26), "obs1": obs_all[i][N:].view(N, h, w, 26),
              "reward": torch.empty(N, dtype=torch.float32, device=dev),
              "shaped0": torch.empty(N, dtype=torch.float32, device=dev),
              "shaped1": torch.empty(N, dtype=torch.float32, device=dev),
-             "done": torch.empty(N, dtype=torch.bool, device=dev)} for _ in range(OBS_SLOTS)]
+             "done": torch.empty(N, dtype=torch.bool, device=dev)} for i in range(OBS_SLOTS)]
+    net = params = pol_out = None
+    if args.policy:
+        from jaxovercooked_b200.policy import ActorCritic
+        assert R == OBS_SLOTS, "--policy reads each env batch's previous observations: needs --rotate == OBS_SLOTS"
+        net = ActorCritic(env.action_space().n, prng_impl="threefry_legacy" if env.prng_mode == 0 else "threefry_partitionable")
+        params = net.init(1234, h * w * 26, device=dev)
+        with torch.no_grad():
+            params["params"]["Dense_2"]["kernel"].mul_(100.0)       # a head that is not near-uniform: actions follow the obs
+        net.bind(params, env=env)
+        cells = [env.empty_cells(N) for _ in range(R)]
+        for b in range(R):
+            outs[b]["cells"] = cells[b]
+        pol_out = [{"action": torch.empty(2 * N, dtype=torch.int32, device=dev), "log_prob": torch.empty(2 * N, dtype=torch.float32, device=dev),
+                    "value": torch.empty(2 * N, dtype=torch.float32, device=dev)} for _ in range(R)]
+        for b in range(R):
+            o = env.get_obs(states[b].env_state if args.log_wrapper else states[b], cells=cells[b])
+            obs_all[b][:N].copy_(o["agent_0"].reshape(N, -1))
+            obs_all[b][N:].copy_(o["agent_1"].reshape(N, -1))
     # synthetic policy: i.i.d. uniform actions, re-drawn on the device for every block of GRAPH_STEPS steps
     # (one graph-safe torch RNG kernel per block; the env never sees the same action tensor twice)
     # Two halves: while the steps of one half run, the next half's actions and subkeys are produced on a side stream
@@ -274,7 +297,8 @@ def run_ours(args):
 
     # per-step subkeys: the callers' `rng, _rng = split(rng)` chain, refreshed for GRAPH_STEPS steps at a time;
     # the per-env `split(_rng, num_envs)` is fused into the step kernel (LazySplit)
-    subkeys = torch.zeros((2, GRAPH_STEPS, 2), dtype=torch.uint32, device=dev)
+    KPS = 2 if args.policy else 1          # subkeys per step: with a policy, one for pi.sample and one for env.step (IPPO_MLP.py:429,447)
+    subkeys = torch.zeros((2, KPS * GRAPH_STEPS, 2), dtype=torch.uint32, device=dev)
     from jaxovercooked_b200 import _lib as oclib
     import ctypes as C
     lib = oclib.load()
@@ -282,8 +306,9 @@ def run_ours(args):
 
     def generate(hf):
         """Fresh i.i.d. actions and the next GRAPH_STEPS subkeys of the `rng, _rng = split(rng)` chain for half `hf`."""
-        act_buf[hf].random_(0, 6)
-        oclib.check(lib.oc_prng_chain(env.prng_mode, chain_rng.data_ptr(), GRAPH_STEPS, subkeys[hf].data_ptr(),
+        if not args.policy:
+            act_buf[hf].random_(0, 6)
+        oclib.check(lib.oc_prng_chain(env.prng_mode, chain_rng.data_ptr(), KPS * GRAPH_STEPS, subkeys[hf].data_ptr(),
                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "oc_prng_chain")
 
     step_no = [0]
@@ -292,11 +317,18 @@ def run_ours(args):
         j = step_no[0]
         step_no[0] += 1
         b, slot = j % R, j % OBS_SLOTS
-        key = ocr.LazySplit(subkeys[hf, i], n_global, first, N)
+        key = ocr.LazySplit(subkeys[hf, KPS * i + KPS - 1], n_global, first, N)
         kw = dict(donate=True, out=outs[slot])
         if args.log_wrapper:
             kw["stats"] = stats
-        _, states[b], _, _, _ = wenv.step(key, states[b], acts[hf][i], **kw)
+        a = acts[hf][i]
+        if args.policy:        # pi, value = network.apply(params, obs_batch); action = pi.sample(seed); log_prob = pi.log_prob(action)
+            if args.policy_input == "cells":    # the env kernel's compact observations: the 26-channel images are not re-read
+                action, _, _ = net.act_cells(params, cells[b], subkeys[hf, KPS * i], out=pol_out[b])
+            else:
+                action, _, _ = net.act(params, obs_all[b], subkeys[hf, KPS * i], out=pol_out[b])
+            a = {"agent_0": action[:N], "agent_1": action[N:]}
+        _, states[b], _, _, _ = wenv.step(key, states[b], a, **kw)
 
     side = torch.cuda.Stream(dev)
 
@@ -351,7 +383,7 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = n_global * K / (ms * 1e-3)
-    launches_per_block = BLOCK + 2          # our kernels: 16 steps + 2 key-chain kernels (the 2 RNG kernels are torch's)
+    launches_per_block = (2 if args.policy else 1) * BLOCK + 2   # our kernels: 16 steps (+ 16 policy forwards) + 2 key-chain kernels (the 2 RNG kernels are torch's)
     gpu_launches = (K // BLOCK) * launches_per_block
 
     # ---- e2e: the C-ABI call with HOST buffers (oc_step_host through env.host_stepper): every step copies that
@@ -359,7 +391,7 @@ def run_ours(args):
     # pinned host memory.  The R env batches run on R streams, so one batch's copies overlap another's kernel; the
     # host waits for a batch's previous results before it reuses that batch's buffers.
     e2e = None
-    if not args.log_wrapper:
+    if not args.log_wrapper and not args.policy:
         Ke = max(2 * R, min(args.e2e_steps, max(args.steps, 2 * R)))
         torch.cuda.synchronize()
         steppers = [env.host_stepper(states[b], n_global, first) for b in range(R)]
@@ -405,7 +437,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_env_step": B_alg, "envs_per_launch": N, "avg_launch_us": step_s * 1e6,
                 "peak_source": peak_src}
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not args.policy:
         n_cpu = min(N, 16384)
         v, cores, n_steps, dt = cpu_rate(lay, args, n_cpu, args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -424,6 +456,13 @@ def run_ours(args):
                        "actions": "i.i.d. uniform {0..5}, re-drawn on the device every 8 steps inside the timed region",
                        "log_wrapper": bool(args.log_wrapper), "parallelism": f"env-sharded x{world}, no per-step comms"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
+    if args.policy:
+        line["metric"] = METRIC + ", rollout step = actor-critic forward + sample + env step"
+        line["roofline"] = None       # two kernels per step; profiles/README.md has each kernel's own numbers
+        line["config"]["actions"] = ("sampled on the device from the actor-critic MLP (architectures/mlp.py, random orthogonal "
+                                     "init, fp16 tensor-core layer 2) evaluated on the previous step's observations")
+        line["config"]["policy_rows_per_step"] = 2 * N
+        line["config"]["policy_input"] = args.policy_input
     if stats is not None:
         line["stats"] = stats.cpu().tolist()
     print(json.dumps(line), flush=True)

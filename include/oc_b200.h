@@ -39,6 +39,7 @@ extern "C" {
 #define OC_MAX_SPECIAL 16            /* pots, goals, onion piles, plate piles: at most 16 each */
 #define OC_PAD 4                     /* agent_view_size - 1 (overcooked.py:88, common.py:153-154) */
 #define OC_OBS_CHANNELS 26           /* overcooked.py:86 */
+#define OC_NUM_CELL_CODES 68         /* record codes: 0..10 objects, 11..34 pot with status 0..23, 35..66 agent (which, dir, held) */
 
 typedef enum {
     OC_OK = 0,
@@ -109,6 +110,15 @@ typedef struct {
     const uint32_t *split_key;
     int64_t split_num;
     int64_t split_first;
+    /* Compact form of the observations this step writes: uint8[N, cell_stride] (oc_layout_info), or NULL.  Per env:
+     *   [0, n_scan)            for each "scan cell" (pots and the counters an agent can face, oc_layout_cell_tables):
+     *                          the code of the record the cell shows, or 0xFF when it shows the layout's static image
+     *   [cell_agents + 2a, +2) agent a: its cell index (y*w + x), then its record code as agent_0 sees it
+     *   [cell_agents + 4]      1 when the urgency plane (channel 25) is set, else 0
+     * Every observation is the static image with those records written over it (agent_1's view: the two agent codes
+     * with bit 4 of (code - 35) flipped), plus channel 25 everywhere when urgent -- oc_policy_forward_cells consumes
+     * this instead of re-reading the 26-channel images. */
+    uint8_t *cells;
 } oc_step_extras;
 
 typedef struct {
@@ -117,6 +127,7 @@ typedef struct {
     int64_t obs_bytes_per_agent;     /* h*w*26        */
     int64_t algorithmic_bytes;       /* 58*h*w + 117 per env-step */
     int32_t envs_per_warp, warps_per_cta, smem_bytes_per_cta;
+    int32_t n_scan, cell_stride, cell_agents;   /* layout of oc_step_extras.cells */
 } oc_layout_info;
 
 /* Build a layout handle on the current CUDA device.
@@ -176,6 +187,12 @@ void oc_host_stepper_destroy(oc_host_stepper *stepper);
 
 /* env.get_obs under vmap: overcooked.py:250-364. */
 int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream);
+/* ... and their compact form as well (see oc_step_extras.cells): what a rollout needs right after oc_reset. */
+int oc_get_obs_cells(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, uint8_t *cells,
+                     void *stream);
+/* Decoding tables of the compact form, into HOST memory (either may be NULL): the 26-byte record of every cell code
+ * (uint8[OC_NUM_CELL_CODES][26], as agent_0 sees it) and the cell index of every scan cell (int32[n_scan]). */
+int oc_layout_cell_tables(const oc_layout *layout, uint8_t *records, int32_t *scan_cells);
 
 /* jax.random.split(key, num)[first : first+count] on the device (callers: IPPO_CL.py:477,535;
  * wrappers/baselines.py:202,207).  `key` is a DEVICE pointer to u32[2]; out u32[count,2] must not alias it.
@@ -217,6 +234,8 @@ typedef struct {
     const uint8_t *obs_template;     /* HOST pointer, uint8[obs_dim], or NULL: an observation most rows are close to
                                         (oc_layout_obs_template); layer 1 is evaluated as a correction to it.  Any
                                         input is handled correctly with any template -- only the speed depends on it */
+    const oc_layout *layout;         /* or NULL.  When given, obs_dim must be h*w*26, the layout's static image is the template
+                                        and oc_policy_forward_cells becomes available; the layout must outlive the policy */
 } oc_policy_desc;
 
 typedef struct oc_policy oc_policy;  /* opaque: the parameters repacked for the kernels, in device memory */
@@ -231,6 +250,14 @@ void oc_policy_destroy(oc_policy *p);
  * are written too.  logits / value / action / log_prob may each be NULL. */
 int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *logits, float *value,
                       const uint32_t *key, int32_t *action, float *log_prob, void *stream);
+
+/* The same for BOTH agents of N environments, read from the compact observations an oc_step / oc_get_obs_cells call
+ * produced (oc_step_extras.cells) instead of the 26-channel images: row m < N is agent_0 of env m, row N + m agent_1
+ * (batchify order), so logits are [2N, action_dim].  Layer 1 becomes base + one precomputed fp16 embedding per
+ * deviating cell; the observations are not read at all.  OC_ERR_UNSUPPORTED_LAYOUT if the policy was created without
+ * a layout or the layout has more than 59 scan cells. */
+int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells, float *logits, float *value,
+                            const uint32_t *key, int32_t *action, float *log_prob, void *stream);
 
 /* The draw alone, for callers that keep `pi` around: action / log_prob (either may be NULL) from logits[M, A]. */
 int oc_policy_sample(int prng_mode, int64_t M, int32_t A, const float *logits, const uint32_t *key, int32_t *action,

@@ -37,26 +37,28 @@ class StatePtrs(C.Structure):
 
 class StepExtras(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in EXTRA_FIELDS] + [("split_key", C.c_void_p), ("split_num", C.c_int64),
-                                                          ("split_first", C.c_int64)]
+                                                          ("split_first", C.c_int64), ("cells", C.c_void_p)]
 
 
 class LayoutInfo(C.Structure):
     _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("n_goal", C.c_int32), ("n_pot", C.c_int32),
                 ("map_bytes_per_env", C.c_int64), ("obs_bytes_per_agent", C.c_int64),
                 ("algorithmic_bytes", C.c_int64),
-                ("envs_per_warp", C.c_int32), ("warps_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32)]
+                ("envs_per_warp", C.c_int32), ("warps_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
+                ("n_scan", C.c_int32), ("cell_stride", C.c_int32), ("cell_agents", C.c_int32)]
 
 
 class PolicyDesc(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("activation", C.c_int32), ("prng_mode", C.c_int32),
-                ("kernel", C.c_void_p * 6), ("bias", C.c_void_p * 6), ("obs_template", C.c_void_p)]
+                ("kernel", C.c_void_p * 6), ("bias", C.c_void_p * 6), ("obs_template", C.c_void_p),
+                ("layout", C.c_void_p)]
 
 
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
            "oc_reset", "oc_step", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
            "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_prng_split", "oc_prng_chain",
-           "oc_policy_create", "oc_policy_update", "oc_policy_destroy", "oc_policy_forward", "oc_policy_sample",
-           "oc_layout_obs_template")
+           "oc_policy_create", "oc_policy_update", "oc_policy_destroy", "oc_policy_forward", "oc_policy_forward_cells", "oc_policy_sample",
+           "oc_layout_obs_template", "oc_get_obs_cells", "oc_layout_cell_tables")
 
 _lib = None
 
@@ -118,8 +120,14 @@ def load():
     lib.oc_policy_destroy.argtypes = [C.c_void_p]
     lib.oc_policy_forward.restype = C.c_int
     lib.oc_policy_forward.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    lib.oc_policy_forward_cells.restype = C.c_int
+    lib.oc_policy_forward_cells.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
     lib.oc_policy_sample.restype = C.c_int
     lib.oc_policy_sample.argtypes = [C.c_int, C.c_int64, C.c_int32] + [C.c_void_p] * 5
+    lib.oc_get_obs_cells.restype = C.c_int
+    lib.oc_get_obs_cells.argtypes = [C.c_void_p, C.c_int64, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oc_layout_cell_tables.restype = C.c_int
+    lib.oc_layout_cell_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oc_layout_obs_template.restype = C.c_int
     lib.oc_layout_obs_template.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib

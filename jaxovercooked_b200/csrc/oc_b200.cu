@@ -41,20 +41,6 @@
 
 // ================================================================================================ host side
 
-struct oc_layout {
-    DevLayout host;
-    DevLayout *dev;
-    int device;
-    int epw;
-    int smem_bytes;
-    int warp_bytes;
-    int warps;                 // warps per CTA: 4 unless the layout's tiles are too big for shared memory
-    int pf_bytes;
-    int tmpl_smem_bytes;       // > 0: the static image (tmpl_k copies) is kept in shared memory
-    unsigned char *tmpl_tile;
-    int num_sms;
-    mutable int occ[3];   // resident CTAs per SM of each kernel mode (filled on first launch)
-};
 
 namespace {
 
@@ -127,18 +113,21 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.pf_bytes = lay->pf_bytes;
     kp.pf_invariant = (((long long)lay->epw * H.map_bytes) % 16 == 0 && (long long)lay->epw * H.map_bytes + 32 < 65536) ? 1 : 0;
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
+    kp.cell_stride = lay->cell_stride; kp.cell_agents = lay->cell_agents;
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
-    if (lay->occ[MODE] == 0) {
-        if (cudaFuncSetAttribute(oc_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    const bool with_cells = kp.cells != nullptr;
+    void (*kern)(const KParams) = with_cells ? oc_env_kernel<MODE, true> : oc_env_kernel<MODE, false>;
+    if (lay->occ[MODE + (with_cells ? 3 : 0)] == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oc_env_kernel<MODE>, lay->warps * 32, lay->smem_bytes) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, lay->smem_bytes) != cudaSuccess)
             return fail_cuda();
-        lay->occ[MODE] = nb < 1 ? 1 : nb;
+        lay->occ[MODE + (with_cells ? 3 : 0)] = nb < 1 ? 1 : nb;
     }
     // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
-    const long long resident = (long long)lay->num_sms * lay->occ[MODE];
+    const long long resident = (long long)lay->num_sms * lay->occ[MODE + (with_cells ? 3 : 0)];
     const long long want = (kp.n_tiles + lay->warps - 1) / lay->warps;
     long long ctas = want;
     if (want > resident) {
@@ -157,7 +146,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, oc_env_kernel<MODE>, kp) == cudaSuccess ? OC_OK : fail_cuda();
+    return cudaLaunchKernelEx(&cfg, kern, kp) == cudaSuccess ? OC_OK : fail_cuda();
 }
 
 }  // namespace
@@ -346,7 +335,9 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->warps = W;
     lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + W * lay->warp_bytes;
     lay->num_sms = prop.multiProcessorCount;
-    lay->occ[0] = lay->occ[1] = lay->occ[2] = 0;
+    lay->cell_agents = (L.n_scan + 1) & ~1;
+    lay->cell_stride = (lay->cell_agents + 5 + 15) & ~15;
+    for (int i = 0; i < 6; ++i) lay->occ[i] = 0;
     lay->device = device;
     {   // tile-sized static observation image
         const size_t eb = (size_t)C * OC_OBS_CHANNELS;
@@ -381,6 +372,16 @@ int oc_layout_query(const oc_layout *lay, oc_layout_info *info) {
     info->obs_bytes_per_agent = (int64_t)L.C * OC_OBS_CHANNELS;
     info->algorithmic_bytes = 58ll * L.C + 117;
     info->envs_per_warp = lay->epw; info->warps_per_cta = lay->warps; info->smem_bytes_per_cta = lay->smem_bytes;
+    info->n_scan = L.n_scan; info->cell_stride = lay->cell_stride; info->cell_agents = lay->cell_agents;
+    return OC_OK;
+}
+
+int oc_layout_cell_tables(const oc_layout *lay, uint8_t *records, int32_t *scan_cells) {
+    if (!lay) return OC_ERR_INVALID_ARG;
+    if (records)
+        for (int c = 0; c < OC_NUM_CELL_CODES; ++c) std::memcpy(records + c * OC_OBS_CHANNELS, lay->host.rec[c], OC_OBS_CHANNELS);
+    if (scan_cells)
+        for (int i = 0; i < lay->host.n_scan; ++i) scan_cells[i] = (int32_t)(lay->host.scan[i] >> 16);
     return OC_OK;
 }
 
@@ -408,12 +409,17 @@ int oc_reset(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state out
 }
 
 int oc_get_obs(const oc_layout *lay, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream_) {
+    return oc_get_obs_cells(lay, N, in, obs0, obs1, nullptr, stream_);
+}
+
+int oc_get_obs_cells(const oc_layout *lay, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, uint8_t *cells,
+                     void *stream_) {
     if (!lay || N < 0 || !state_ok(in) || !obs0 || !obs1) return OC_ERR_INVALID_ARG;
     if (N == 0) return OC_OK;
     if (!state_aligned(in)) return OC_ERR_ALIGNMENT;
     KParams kp;
     std::memset(&kp, 0, sizeof(kp));
-    kp.N = N; kp.st = in; kp.obs0 = obs0; kp.obs1 = obs1;
+    kp.N = N; kp.st = in; kp.obs0 = obs0; kp.obs1 = obs1; kp.cells = cells;
     kp.bulk_ok = aligned16(obs0) && aligned16(obs1);
     return launch_env<MODE_OBS>(lay, kp, static_cast<cudaStream_t>(stream_));
 }
@@ -458,7 +464,7 @@ int oc_step(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state in, 
     kp.N = N; kp.keys = keys; kp.st = out; kp.act0 = act0; kp.act1 = act1; kp.obs0 = obs0; kp.obs1 = obs1;
     kp.reward = reward; kp.shaped0 = shaped0; kp.shaped1 = shaped1; kp.done = done;
     if (reset_state) { kp.rs = *reset_state; kp.has_rs = 1; }
-    if (extras) kp.ex = *extras;
+    if (extras) { kp.ex = *extras; kp.cells = extras->cells; }
     kp.bulk_ok = aligned16(obs0) && aligned16(obs1);
     return launch_env<MODE_STEP>(lay, kp, stream);
 }

@@ -50,6 +50,8 @@ struct KParams {
     float *reward, *shaped0, *shaped1;
     uint8_t *done;
     oc_step_extras ex;
+    uint8_t *cells;       // compact observation (scan-cell codes, agent cells, urgency), or NULL
+    int cell_stride, cell_agents;
     int epw;        // environments per warp tile: 16, 8, 4 or 2
     int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
     int warp_bytes; // shared memory per warp
@@ -65,3 +67,20 @@ struct KParams {
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBS = 2 };
 
 }  // namespace
+
+struct oc_layout {
+    DevLayout host;
+    DevLayout *dev;
+    int device;
+    int epw;
+    int smem_bytes;
+    int warp_bytes;
+    int warps;                 // warps per CTA: 4 unless the layout's tiles are too big for shared memory
+    int pf_bytes;
+    int tmpl_smem_bytes;       // > 0: the static image (tmpl_k copies) is kept in shared memory
+    unsigned char *tmpl_tile;
+    int num_sms;
+    int cell_stride, cell_agents;   // compact observation: bytes per env, offset of the agent entries (oc_step_extras.cells)
+    mutable int occ[6];   // resident CTAs per SM of each kernel mode (filled on first launch)
+};
+

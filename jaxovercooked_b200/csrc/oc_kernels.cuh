@@ -8,7 +8,9 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ kernel
 
-template <int MODE>
+// CELLS: also emit the compact form of the observations (oc_step_extras.cells); a separate instantiation so that the
+// plain kernel keeps its register budget
+template <int MODE, bool CELLS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
@@ -395,11 +397,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     const int o = c[0], st = c[2];
                     if (o == 8 ? (st != 23) : (o != 2 && o != 10))
                         stage_record(el * C + (int)(sc >> 16), (o == 8) ? kCodePot + min(st, 23) : min(o, 10));
+                    if (CELLS)     // the compact form of this observation (include/oc_b200.h, oc_step_extras.cells)
+                        p.cells[(env0 + el) * p.cell_stride + (f - el * p.n_scan)] =
+                            (uint8_t)((o == 8 ? (st != 23) : (o != 2 && o != 10)) ? ((o == 8) ? kCodePot + min(st, 23) : min(o, 10)) : 0xff);
                 }
             }
             __syncwarp();
             // (4c) agent cells show the agent, its direction and what it holds (:313-323, :345-353)
             if (active) stage_record(es * C + ny * w + nx, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)));
+            if (CELLS && active) {
+                uint8_t *cl = p.cells + env * p.cell_stride + p.cell_agents;
+                const int code = kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2));
+                *reinterpret_cast<unsigned short *>(cl + 2 * ai) = (unsigned short)((ny * w + nx) | (code << 8));
+                if (ai == 0) cl[4] = urg ? 1 : 0;
+            }
             __syncwarp();
             // (4d) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left
             {

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <new>
 
+#include "oc_common.cuh"
 #include "threefry.cuh"
 
 namespace {
@@ -39,9 +40,9 @@ constexpr int kTileM = 128;
 constexpr int kPolWarps = 16;
 constexpr int kPolThreads = kPolWarps * 32;
 constexpr int kListCap = 512;                 // (k, delta) entries per warp between two flushes
-constexpr int kListWords = kListCap + 4;      // + padding to a multiple of 4 entries
+constexpr int kListWords = kListCap + 8;      // + padding to a multiple of 8 entries
 constexpr int kNetBytes = kTileM * kHid * 2;  // one fp16 128x128 operand image: 32 KB = 2 swizzle atoms of 16 KB
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;               // two accumulator buffers of 256 columns (actor | critic)
 
 struct PolicySmall {
     float base[kHid2];          // Dense_0/Dense_3 bias + template . kernel
@@ -63,11 +64,11 @@ constexpr int kOffHpC = kOffHpA + kTileM * 2 * 8 * 4;
 constexpr int kOffList = kOffHpC + kTileM * 2 * 4;
 constexpr int kOffMask = kOffList + kPolWarps * kListWords * 4;
 constexpr int kOffBar = kOffMask + 16 * 2 * 16;
-constexpr int kOffTmpl = kOffBar + 16;
+constexpr int kOffTmpl = kOffBar + 32;
 static_assert(kOffHpA % 16 == 0 && kOffList % 16 == 0 && kOffMask % 16 == 0 && kOffTmpl % 16 == 0, "alignment");
 
 struct PParams {
-    const float *w1;            // [K][256] fp32
+    const __half *w1;           // [K][256] fp16
     const uint8_t *w2img;       // 2 x 32 KB fp16 images (swizzled, K-major, row = output unit)
     const PolicySmall *small;
     const uint8_t *tmpl;        // [K]
@@ -80,6 +81,12 @@ struct PParams {
     float *logits, *value, *log_prob;
     const uint32_t *key;
     int32_t *action;
+    // compact-observation source (oc_policy_forward_cells): rows [0, N) are agent_0's views, [N, 2N) agent_1's
+    const uint8_t *cells;       // [N][cell_stride]
+    const __half *emb;          // [C*68 + 2][256] fp16: layer-1 contribution of (cell, code as the viewer sees it); then a zero row, the urgency row
+    const uint8_t *scan_cells;  // [n_scan] cell index of every scan slot
+    long long N;
+    int cell_stride, cell_agents, n_scan, C;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,72 +137,144 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // Categorical(logits).sample(seed=key) and .log_prob(action) for one row (distrax over jax.random.categorical):
 // action = argmax_a(logits[a] + gumbel(key, (1, M, A))[0, row, a]), first maximum wins; log_prob = log_softmax(logits)[action]
-__device__ __forceinline__ void sample_row(int part, uint32_t k0, uint32_t k1, int n, long long row, int A,
-                                           const float (&lg)[OC_POLICY_MAX_ACTIONS], int &arg, float &lp) {
-    float best = 0.f, mx = lg[0];
-    arg = 0;
+// Four consecutive lanes share a row: lane part `s` draws the noise of actions s and s + 4, a 4-lane butterfly picks the winner.
+__device__ __forceinline__ float gumbel_at(int part, uint32_t k0, uint32_t k1, int n, int j) {
+    // jax.random.gumbel: -log(-log(uniform(key, shape, minval=tiny, maxval=1)))
+    const uint32_t bits = bits_at(part, k0, k1, n, j);
+    const float f = __uint_as_float((bits >> 9) | 0x3f800000u) - 1.0f;
+    const float u = fmaxf(1.17549435e-38f, f + 1.17549435e-38f);
+    return -logf(-logf(u));
+}
+
+__device__ __forceinline__ void sample_row4(int part, uint32_t k0, uint32_t k1, int n, long long row, int A, int s,
+                                            const float (&lg)[OC_POLICY_MAX_ACTIONS], int &arg, float &lp) {
+    float best = -INFINITY;
+    arg = OC_POLICY_MAX_ACTIONS;
 #pragma unroll
-    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a) {
+    for (int h = 0; h < 2; ++h) {
+        const int a = s + 4 * h;
         if (a < A) {
-            // jax.random.gumbel: -log(-log(uniform(key, shape, minval=tiny, maxval=1)))
-            const uint32_t bits = bits_at(part, k0, k1, n, (int)(row * A + a));
-            const float f = __uint_as_float((bits >> 9) | 0x3f800000u) - 1.0f;
-            const float u = fmaxf(1.17549435e-38f, f + 1.17549435e-38f);
-            const float z = lg[a] - logf(-logf(u));
-            if (a == 0 || z > best) { best = z; arg = a; }
-            mx = fmaxf(mx, lg[a]);
+            float l = 0.f;
+#pragma unroll
+            for (int q = 0; q < OC_POLICY_MAX_ACTIONS; ++q) if (q == a) l = lg[q];
+            const float z = l + gumbel_at(part, k0, k1, n, (int)(row * A + a));
+            if (arg == OC_POLICY_MAX_ACTIONS || z > best) { best = z; arg = a; }
         }
     }
-    float s = 0.f, la = 0.f;
 #pragma unroll
-    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
-        if (a < A) { s += expf(lg[a] - mx); if (a == arg) la = lg[a]; }
-    lp = la - (mx + logf(s));
+    for (int d = 1; d < 4; d <<= 1) {
+        const float zo = __shfl_xor_sync(0xffffffffu, best, d);
+        const int ao = __shfl_xor_sync(0xffffffffu, arg, d);
+        if (ao < OC_POLICY_MAX_ACTIONS && (arg == OC_POLICY_MAX_ACTIONS || zo > best || (zo == best && ao < arg))) { best = zo; arg = ao; }
+    }
+    float mx = lg[0];
+#pragma unroll
+    for (int q = 1; q < OC_POLICY_MAX_ACTIONS; ++q) if (q < A) mx = fmaxf(mx, lg[q]);
+    float sum = 0.f, la = 0.f;
+#pragma unroll
+    for (int q = 0; q < OC_POLICY_MAX_ACTIONS; ++q)
+        if (q < A) { sum += expf(lg[q] - mx); if (q == arg) la = lg[q]; }
+    lp = la - (mx + logf(sum));
 }
 
 __global__ void oc_policy_sample_kernel(int part, long long M, int A, const float *__restrict__ logits,
                                         const uint32_t *__restrict__ key, int32_t *action, float *log_prob) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= M) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = t >> 2;
+    const bool live = row < M;
     float lg[OC_POLICY_MAX_ACTIONS];
 #pragma unroll
-    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a) lg[a] = a < A ? logits[row * A + a] : 0.f;
+    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a) lg[a] = (live && a < A) ? logits[row * A + a] : 0.f;
     int arg;
     float lp;
-    sample_row(part, __ldg(key), __ldg(key + 1), (int)(M * A), row, A, lg, arg, lp);
-    if (action) action[row] = arg;
-    if (log_prob) log_prob[row] = lp;
+    sample_row4(part, __ldg(key), __ldg(key + 1), (int)(M * A), live ? row : 0, A, (int)(t & 3), lg, arg, lp);
+    if (live && (t & 3) == 0) {
+        if (action) action[row] = arg;
+        if (log_prob) log_prob[row] = lp;
+    }
 }
 
-// accumulate `n` (k, delta) entries of this warp's list: acc[0..7] += delta * W1[k, 8*lane .. 8*lane+7]
-__device__ __forceinline__ void gather_rows(const float *__restrict__ w1, uint32_t *list, int n, int lane, float (&acc)[8]) {
-    if (lane < 3) list[n + lane] = 0u;       // pad to a multiple of 4 with (k=0, delta=0)
+// acc0 += lo(w) * d, acc1 += hi(w) * d with fp16 operands and fp32 accumulation (one FHFMA each on sm_100)
+__device__ __forceinline__ void fma_h2(float &acc0, float &acc1, uint32_t w, unsigned short d) {
+    asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %3, %0;\n\tfma.rn.f32.f16 %1, hi, %3, %1;\n\t}\n"
+        : "+f"(acc0), "+f"(acc1) : "r"(w), "h"(d));
+}
+
+// accumulate `n` entries (k << 16 | fp16 delta) of this warp's list: acc[0..7] += delta * W1[k, 8*lane .. 8*lane+7]
+// (W1 is stored as fp16 rows of 512 bytes: one 16-byte load per lane and entry, eight entries in flight)
+__device__ __forceinline__ void gather_rows(const __half *__restrict__ w1, uint32_t *list, int n, int lane, float (&acc)[8]) {
+    if (lane < 7) list[n + lane] = 0u;       // pad to a multiple of 8 with (k=0, delta=0)
     __syncwarp();
-    const float *wl = w1 + 8 * lane;
-    for (int i = 0; i < n; i += 4) {
-        const uint4 e4 = *reinterpret_cast<const uint4 *>(list + i);
-        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
-        float4 wa[4], wb[4];
+    const __half *wl = w1 + 8 * lane;
+    for (int i = 0; i < n; i += 8) {
+        const uint4 ea = *reinterpret_cast<const uint4 *>(list + i), eb = *reinterpret_cast<const uint4 *>(list + i + 4);
+        const uint32_t e[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+        uint4 w[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 *wp = reinterpret_cast<const float4 *>(wl + (size_t)(e[u] >> 16) * kHid2);
-            wa[u] = __ldg(wp);
-            wb[u] = __ldg(wp + 1);
-        }
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint4 *>(wl + (e[u] >> 16) * kHid2));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float d = (float)(short)(e[u] & 0xffffu);
-            acc[0] = fmaf(d, wa[u].x, acc[0]); acc[1] = fmaf(d, wa[u].y, acc[1]);
-            acc[2] = fmaf(d, wa[u].z, acc[2]); acc[3] = fmaf(d, wa[u].w, acc[3]);
-            acc[4] = fmaf(d, wb[u].x, acc[4]); acc[5] = fmaf(d, wb[u].y, acc[5]);
-            acc[6] = fmaf(d, wb[u].z, acc[6]); acc[7] = fmaf(d, wb[u].w, acc[7]);
+        for (int u = 0; u < 8; ++u) {
+            const unsigned short d = (unsigned short)(e[u] & 0xffffu);
+            fma_h2(acc[0], acc[1], w[u].x, d);
+            fma_h2(acc[2], acc[3], w[u].y, d);
+            fma_h2(acc[4], acc[5], w[u].z, d);
+            fma_h2(acc[6], acc[7], w[u].w, d);
         }
     }
     __syncwarp();
 }
 
-template <int ACT>
+// this lane's 16-byte pieces of one observation row (piece 32*g + lane), issued together so that one DRAM round trip
+// covers the row; rows past the end load nothing.  Row `row_l` of tile `tile` starts at byte a0 + (tile*128 + row_l)*K of
+// the 16-byte aligned stream; tile*128*K is a multiple of 16, so everything but the tile offset is 32-bit arithmetic.
+template <int PL>
+__device__ __forceinline__ void load_row(const PParams &p, long long tile, int row_l, int lane, uint4 (&pf)[PL]) {
+    if (tile < p.n_tiles && tile * kTileM + row_l < p.M) {
+        const int local = p.a0 + row_l * p.K;
+        const int np = ((local & 15) + p.K + 15) >> 4;
+        const uint4 *src = p.obs16 + tile * (long long)(kTileM / 16 * p.K) + (local >> 4);
+#pragma unroll
+        for (int g = 0; g < PL; ++g) {
+            const int q = g * 32 + lane;
+            pf[g] = q < np ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
+// append the differing bytes of one 16-byte piece to the list: entry = k << 16 | fp16(obs - template); bytes that belong
+// to a neighbouring row (k outside [0, K)) become the neutral entry 0
+__device__ __forceinline__ int emit_piece(uint32_t *list, int pos, const uint4 &o, const uint4 &t, const uint32_t (&mw)[4], int kbase, int K) {
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t mm = mw[i];
+        while (mm) {
+            const int sh = __ffs(mm) - 8;                 // bit 7 of byte b -> shift 8*b
+            mm &= mm - 1;
+            const int k = kbase + 4 * i + (sh >> 3);
+            const int dlt = (int)((ow[i] >> sh) & 255u) - (int)((tw[i] >> sh) & 255u);
+            const uint32_t e = ((uint32_t)k << 16) | (uint32_t)__half_as_ushort(__int2half_rn(dlt));
+            list[pos++] = (unsigned)k < (unsigned)K ? e : 0u;
+        }
+    }
+    return pos;
+}
+
+// this lane's bytes of one env's compact observation (slots lane and lane + 32)
+__device__ __forceinline__ void load_cells(const PParams &p, long long tile, int row_l, int lane, uint32_t (&cb)[2]) {
+    const long long row = tile * kTileM + row_l;
+    if (tile < p.n_tiles && row < p.M) {
+        const uint8_t *src = p.cells + (row >= p.N ? row - p.N : row) * p.cell_stride;
+        cb[0] = lane < p.cell_stride ? __ldg(src + lane) : 0xffu;
+        cb[1] = lane + 32 < p.cell_stride ? __ldg(src + lane + 32) : 0xffu;
+    }
+}
+
+// PL > 0: rows are uint8 observations, PL 16-byte pieces per lane and row.  PL == 0: rows come from the env kernel's
+// compact observations (cells) and layer 1 is a sum of precomputed (view, cell, code) embeddings.
+template <int ACT, int PL>
 __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams p) {
+    constexpr int PLA = PL > 0 ? PL : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = sm + kOffA;
@@ -204,9 +283,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
     float *hpA = reinterpret_cast<float *>(sm + kOffHpA);      // [128][2][8]
     float *hpC = reinterpret_cast<float *>(sm + kOffHpC);      // [128][2]
     uint32_t *lists = reinterpret_cast<uint32_t *>(sm + kOffList);
-    uint4 *masks = reinterpret_cast<uint4 *>(sm + kOffMask);   // [nvar][first, last]
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + kOffBar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 16);
     uint8_t *tmplv = sm + kOffTmpl;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -220,18 +298,17 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
         const uint4 *s2 = reinterpret_cast<const uint4 *>(p.small);
         uint4 *d2 = reinterpret_cast<uint4 *>(sS);
         for (int i = tid; i < (int)sizeof(PolicySmall) / 16; i += kPolThreads) d2[i] = __ldg(s2 + i);
-        const int g = 1 << p.gshift;
-        for (int i = tid; i < p.nvar * p.tv_stride; i += kPolThreads) {
-            const int v = i / p.tv_stride, j = i - v * p.tv_stride;
-            const int a = (p.a0 + v * g) & 15;
-            tmplv[i] = (j >= a && j < a + K) ? __ldg(p.tmpl + (j - a)) : (uint8_t)0;
-        }
-        uint8_t *mb = reinterpret_cast<uint8_t *>(masks);
-        for (int i = tid; i < p.nvar * 32; i += kPolThreads) {
-            const int v = i >> 5, j = i & 15, last = (i >> 4) & 1;
-            const int a = (p.a0 + v * g) & 15;
-            const int e = ((a + K - 1) & 15) + 1;
-            mb[i] = last ? (j < e ? 0xff : 0) : (j >= a ? 0xff : 0);
+        // template variants: variant v is the template repeated periodically, shifted so that a row whose first byte sits at
+        // offset a_v inside its first 16-byte piece lines up with 16-byte reads (bytes of the neighbouring rows cancel too)
+        if (PL > 0) {
+            const int g = 1 << p.gshift;
+            for (int i = tid; i < p.nvar * p.tv_stride; i += kPolThreads) {
+                const int v = i / p.tv_stride, j = i - v * p.tv_stride;
+                const int a = (p.a0 + v * g) & 15;
+                tmplv[i] = __ldg(p.tmpl + (j - a + K) % K);
+            }
+        } else {
+            for (int i = tid; i < p.n_scan; i += kPolThreads) sm[kOffMask + i] = __ldg(p.scan_cells + i);
         }
     }
     if (warp == 0) {
@@ -240,6 +317,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
     }
     if (tid == 32) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_addr(mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_addr(mbar) + 8) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // W2 image: generic-proxy writes -> tensor-core reads
@@ -248,84 +326,283 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t sA_u = smem_addr(sA), sW2_u = smem_addr(sW2), bar_u = smem_addr(mbar);
-    uint32_t phase = 0;
     uint32_t *list = lists + warp * kListWords;
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        // ------------------------------------------------------------------ layer 1: one row per warp, 8 rounds
-        for (int rr = 0; rr < kTileM / kPolWarps; ++rr) {
-            const int row_l = rr * kPolWarps + warp;
-            const long long row = (long long)tile * kTileM + row_l;
-            float acc[8];
-            {
-                const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
-                const float4 b1 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane + 4);
-                acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-                acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-            }
-            if (row < p.M) {
-                const long long fo = row * K + p.a0;
-                const int a = (int)(fo & 15);
-                const int np = (a + K + 15) >> 4;
-                const int v = ((a - p.a0) & 15) >> p.gshift;
-                const uint4 *src = p.obs16 + (fo >> 4);
-                const uint8_t *tv = tmplv + v * p.tv_stride;
-                int n = 0;
-                for (int g0 = 0; g0 < np; g0 += 32) {
-                    const int q = g0 + lane;
-                    uint4 o = make_uint4(0, 0, 0, 0), t = o;
-                    if (q < np) {
-                        o = __ldg(src + q);
-                        t = *reinterpret_cast<const uint4 *>(tv + 16 * q);
-                    }
-                    uint4 x = make_uint4(o.x ^ t.x, o.y ^ t.y, o.z ^ t.z, o.w ^ t.w);
-                    if (q == 0) { const uint4 m = masks[2 * v]; x.x &= m.x; x.y &= m.y; x.z &= m.z; x.w &= m.w; }
-                    if (q == np - 1) { const uint4 m = masks[2 * v + 1]; x.x &= m.x; x.y &= m.y; x.z &= m.z; x.w &= m.w; }
-                    const uint32_t m0 = nz_bytes(x.x), m1 = nz_bytes(x.y), m2 = nz_bytes(x.z), m3 = nz_bytes(x.w);
-                    const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-                    if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
-                    int incl = cnt;
+    // Each warp walks the rows rr*16 + warp (rr = 0..7) of its CTA's tiles; the observation pieces of the next two
+    // rows are always in flight in registers (pfA / pfB), also across the tile boundary and the layer-2 phase.
+    int item = 0;
+    uint4 pfA[PLA], pfB[PLA];
+    uint32_t cbA[2] = {0xffu, 0xffu}, cbB[2] = {0xffu, 0xffu};
+    if (PL > 0) {
+        load_row<PLA>(p, blockIdx.x, warp, lane, pfA);
+        load_row<PLA>(p, blockIdx.x, kPolWarps + warp, lane, pfB);
+    } else {
+        load_cells(p, blockIdx.x, warp, lane, cbA);
+        load_cells(p, blockIdx.x, kPolWarps + warp, lane, cbB);
+    }
+    uint8_t *s_sc = reinterpret_cast<uint8_t *>(sm + kOffMask);          // [n_scan] scan slot -> cell (cells source only)
+
+    auto finish_row = [&](const int row_l, float (&acc)[8]) {
+        // activation, fp16, swizzled K-major store: lane -> net = lane >> 4, 16-byte chunk j = lane & 15 of the row
+        uint4 pk;
+        {
+            const __half2 h0 = __floats2half2_rn(activate<ACT>(acc[0]), activate<ACT>(acc[1]));
+            const __half2 h1 = __floats2half2_rn(activate<ACT>(acc[2]), activate<ACT>(acc[3]));
+            const __half2 h2 = __floats2half2_rn(activate<ACT>(acc[4]), activate<ACT>(acc[5]));
+            const __half2 h3 = __floats2half2_rn(activate<ACT>(acc[6]), activate<ACT>(acc[7]));
+            pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+            pk.z = *reinterpret_cast<const uint32_t *>(&h2); pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+        }
+        const int j = lane & 15;
+        uint8_t *dst = sA + (lane >> 4) * kNetBytes + (j >> 3) * (kNetBytes / 2) + row_l * 128 + (((j & 7) ^ (row_l & 7)) << 4);
+        *reinterpret_cast<uint4 *>(dst) = pk;
+    };
+
+    // layer 1 of one row from its compact observation: base + sum of the embeddings of the deviating cells
+    auto do_row_cells = [&](uint32_t (&cb)[2], const long long tile, const int rr) {
+        const int row_l = rr * kPolWarps + warp;
+        const long long row = tile * kTileM + row_l;
+        float acc[8];
+        {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane + 4);
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+            acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+        if (row < p.M) {
+            const int view = row >= p.N ? 1 : 0;
+            const int idx_zero = p.C * OC_NUM_CELL_CODES;
+            int idx[2];
+            unsigned bal[2];
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += up;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (n + total > kListCap) {          // a dense row: drain what is pending first
-                        gather_rows(p.w1, list, n, lane, acc);
-                        n = 0;
-                    }
-                    int pos = n + incl - cnt;
-                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, tw[4] = {t.x, t.y, t.z, t.w}, mw[4] = {m0, m1, m2, m3};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t mm = mw[i];
-                        while (mm) {
-                            const int sh = __ffs(mm) - 8;                 // bit 7 of byte b -> shift 8*b
-                            mm &= mm - 1;
-                            const int k = 16 * q + 4 * i + (sh >> 3) - a;
-                            const int dlt = (int)((ow[i] >> sh) & 255u) - (int)((tw[i] >> sh) & 255u);
-                            list[pos++] = ((uint32_t)k << 16) | ((uint32_t)dlt & 0xffffu);
-                        }
-                    }
-                    n += total;
-                    __syncwarp();
+            for (int g = 0; g < 2; ++g) {
+                const int slot = g * 32 + lane;
+                const int b = (int)cb[g];
+                const int prev = (int)__shfl_up_sync(0xffffffffu, cb[g], 1);     // an agent's cell sits one slot before its code
+                const int ag = slot - p.cell_agents;
+                bool valid = false;
+                int ix = idx_zero;
+                if (slot < p.n_scan) {
+                    valid = b != 0xff;
+                    ix = (int)s_sc[slot] * OC_NUM_CELL_CODES + b;
+                } else if (ag == 1 || ag == 3) {
+                    valid = true;
+                    ix = prev * OC_NUM_CELL_CODES + (view ? kCodeAgent + ((b - kCodeAgent) ^ 16) : b);
+                } else if (ag == 4) {
+                    valid = b != 0;
+                    ix = idx_zero + 1;
                 }
-                gather_rows(p.w1, list, n, lane, acc);
+                idx[g] = ix;
+                bal[g] = __ballot_sync(0xffffffffu, valid);
             }
-            // activation, fp16, swizzled K-major store: lane -> net = lane >> 4, 16-byte chunk j = lane & 15 of the row
-            uint4 pk;
-            {
-                const __half2 h0 = __floats2half2_rn(activate<ACT>(acc[0]), activate<ACT>(acc[1]));
-                const __half2 h1 = __floats2half2_rn(activate<ACT>(acc[2]), activate<ACT>(acc[3]));
-                const __half2 h2 = __floats2half2_rn(activate<ACT>(acc[4]), activate<ACT>(acc[5]));
-                const __half2 h3 = __floats2half2_rn(activate<ACT>(acc[6]), activate<ACT>(acc[7]));
-                pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
-                pk.z = *reinterpret_cast<const uint32_t *>(&h2); pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+            {   // this slot is free again: fetch the row after next
+                const int it2 = item + 2;
+                load_cells(p, (long long)blockIdx.x + (long long)(it2 >> 3) * gridDim.x, (it2 & 7) * kPolWarps + warp, lane, cb);
             }
-            const int j = lane & 15;
-            uint8_t *dst = sA + (lane >> 4) * kNetBytes + (j >> 3) * (kNetBytes / 2) + row_l * 128 + (((j & 7) ^ (row_l & 7)) << 4);
-            *reinterpret_cast<uint4 *>(dst) = pk;
+            const __half *el = p.emb + 8 * lane;
+            while (bal[0] | bal[1]) {                      // four embeddings in flight, in slot order (deterministic sum)
+                uint4 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int ix = idx_zero;
+                    if (bal[0]) { const int src = __ffs(bal[0]) - 1; bal[0] &= bal[0] - 1; ix = __shfl_sync(0xffffffffu, idx[0], src); }
+                    else if (bal[1]) { const int src = __ffs(bal[1]) - 1; bal[1] &= bal[1] - 1; ix = __shfl_sync(0xffffffffu, idx[1], src); }
+                    w[u] = __ldg(reinterpret_cast<const uint4 *>(el + (size_t)ix * kHid2));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    fma_h2(acc[0], acc[1], w[u].x, (unsigned short)0x3c00);
+                    fma_h2(acc[2], acc[3], w[u].y, (unsigned short)0x3c00);
+                    fma_h2(acc[4], acc[5], w[u].z, (unsigned short)0x3c00);
+                    fma_h2(acc[6], acc[7], w[u].w, (unsigned short)0x3c00);
+                }
+            }
+        } else {
+            const int it2 = item + 2;
+            load_cells(p, (long long)blockIdx.x + (long long)(it2 >> 3) * gridDim.x, (it2 & 7) * kPolWarps + warp, lane, cb);
+        }
+        ++item;
+        finish_row(row_l, acc);
+    };
+
+    auto do_row = [&](uint4 (&pf)[PLA], const long long tile, const int rr) {
+        const int row_l = rr * kPolWarps + warp;
+        float acc[8];
+        {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane + 4);
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+            acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+        int n = 0;
+        if (tile * kTileM + row_l < p.M) {
+            const int local = p.a0 + row_l * K;
+            const int a = local & 15;
+            const int np = (a + K + 15) >> 4;
+            const uint8_t *tv = tmplv + (((a - p.a0) & 15) >> p.gshift) * p.tv_stride;
+            uint4 t[PLA];
+            uint32_t mw[PLA][4];
+            int cnt = 0;
+#pragma unroll
+            for (int g = 0; g < PLA; ++g) {
+                const int q = g * 32 + lane;
+                t[g] = make_uint4(0u, 0u, 0u, 0u);
+                if (q < np) t[g] = *reinterpret_cast<const uint4 *>(tv + 16 * q);
+                mw[g][0] = nz_bytes(pf[g].x ^ t[g].x); mw[g][1] = nz_bytes(pf[g].y ^ t[g].y);
+                mw[g][2] = nz_bytes(pf[g].z ^ t[g].z); mw[g][3] = nz_bytes(pf[g].w ^ t[g].w);
+                cnt += __popc(mw[g][0]) + __popc(mw[g][1]) + __popc(mw[g][2]) + __popc(mw[g][3]);
+            }
+            if (__ballot_sync(0xffffffffu, cnt != 0) != 0u) {
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total <= kListCap) {                 // the usual case: a handful of entries for the whole row
+                    int pos = incl - cnt;
+                    if (cnt) {
+#pragma unroll
+                        for (int g = 0; g < PLA; ++g) pos = emit_piece(list, pos, pf[g], t[g], mw[g], 16 * (g * 32 + lane) - a, K);
+                    }
+                    n = total;
+                } else {                                  // a dense row: one piece per lane at a time, draining the list as it fills
+#pragma unroll
+                    for (int g = 0; g < PLA; ++g) {
+                        const int c = __popc(mw[g][0]) + __popc(mw[g][1]) + __popc(mw[g][2]) + __popc(mw[g][3]);
+                        int inc2 = c;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int up = __shfl_up_sync(0xffffffffu, inc2, d);
+                            if (lane >= d) inc2 += up;
+                        }
+                        const int tot2 = __shfl_sync(0xffffffffu, inc2, 31);
+                        if (n + tot2 > kListCap) {
+                            gather_rows(p.w1, list, n, lane, acc);
+                            n = 0;
+                        }
+                        emit_piece(list, n + inc2 - c, pf[g], t[g], mw[g], 16 * (g * 32 + lane) - a, K);
+                        n += tot2;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        {   // this slot is free again: fetch the row after next
+            const int it2 = item + 2;
+            load_row<PLA>(p, (long long)blockIdx.x + (long long)(it2 >> 3) * gridDim.x, (it2 & 7) * kPolWarps + warp, lane, pf);
+            ++item;
+        }
+        if (n) gather_rows(p.w1, list, n, lane, acc);
+        finish_row(row_l, acc);
+    };
+
+    auto mbar_wait = [&](uint32_t bar, uint32_t parity) {
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            if (!done && ++spins > (1u << 26)) __trap();      // a lost MMA completion must not hang the GPU
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    };
+    // heads: TMEM quadrant (warp & 3), 64-column group (warp >> 2) of accumulator buffer `buf`
+    auto do_heads = [&](const int buf) {
+    {
+        const int qd = warp & 3, grp = warp >> 2, net = grp >> 1, half = grp & 1;
+        const int row_l = 32 * qd + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(buf * kHid2 + net * kHid + half * 64);
+        if (net == 0) {
+            float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float v[16];
+                tmem_ld16(taddr + cc * 16, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = half * 64 + cc * 16 + i;
+                    const float h = activate<ACT>(v[i] + sS->b2[c]);
+                    const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
+                    const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
+                    pa[0] = fmaf(h, wlo.x, pa[0]); pa[1] = fmaf(h, wlo.y, pa[1]);
+                    pa[2] = fmaf(h, wlo.z, pa[2]); pa[3] = fmaf(h, wlo.w, pa[3]);
+                    pa[4] = fmaf(h, whi.x, pa[4]); pa[5] = fmaf(h, whi.y, pa[5]);
+                    pa[6] = fmaf(h, whi.z, pa[6]); pa[7] = fmaf(h, whi.w, pa[7]);
+                }
+            }
+            float4 *o = reinterpret_cast<float4 *>(hpA + (row_l * 2 + half) * 8);
+            o[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+            o[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
+        } else {
+            float pc = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float v[16];
+                tmem_ld16(taddr + cc * 16, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = half * 64 + cc * 16 + i;
+                    pc = fmaf(activate<ACT>(v[i] + sS->b2[kHid + c]), sS->cw[c], pc);
+                }
+            }
+            hpC[row_l * 2 + half] = pc;
+        }
+    }
+    };
+    // finish the rows of `tile`: logits, value, categorical draw (4 threads per row)
+    auto do_finish = [&](const long long tile) {
+    {
+        const int row_l = tid >> 2, s4 = tid & 3;
+        const long long row = (long long)tile * kTileM + row_l;
+        const bool live = row < p.M;
+        const int A = p.A;
+        float lg[OC_POLICY_MAX_ACTIONS];
+#pragma unroll
+        for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
+            lg[a] = hpA[(row_l * 2) * 8 + a] + hpA[(row_l * 2 + 1) * 8 + a] + sS->b3[a];
+        if (live && s4 == 0) {
+            if (p.logits) {
+#pragma unroll
+                for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
+                    if (a < A) p.logits[row * A + a] = lg[a];
+            }
+            if (p.value) p.value[row] = hpC[row_l * 2] + hpC[row_l * 2 + 1] + sS->b3c;
+        }
+        if (p.key) {
+            int arg;
+            float lp;
+            sample_row4(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(p.M * A), live ? row : 0, A, s4, lg, arg, lp);
+            if (live && s4 == 0) {
+                if (p.action) p.action[row] = arg;
+                if (p.log_prob) p.log_prob[row] = lp;
+            }
+        }
+    }
+    };
+
+    // Software pipeline over this CTA's tiles: while the tensor cores run layer 2 of tile t into one half of TMEM, the
+    // warps do the heads of tile t-1 from the other half and then layer 1 of tile t+1.
+    uint32_t phase0 = 0, phase1 = 0;
+    long long prev = -1;
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
+        if (prev >= 0) {          // layer 2 of the previous tile has finished reading the A tile (and its accumulators are ready)
+            if (buf) { mbar_wait(bar_u, phase0); phase0 ^= 1u; } else { mbar_wait(bar_u + 8, phase1); phase1 ^= 1u; }
+        }
+        // ------------------------------------------------------------------ layer 1: one row per warp, 8 rounds
+#pragma unroll 1
+        for (int rr = 0; rr < kTileM / kPolWarps; rr += 2) {
+            if (PL > 0) {
+                do_row(pfA, tile, rr);
+                do_row(pfB, tile, rr + 1);
+            } else {
+                do_row_cells(cbA, tile, rr);
+                do_row_cells(cbB, tile, rr + 1);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
@@ -338,93 +615,23 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
 #pragma unroll
                 for (int ks = 0; ks < kHid / 16; ++ks) {
                     const uint32_t off = net * kNetBytes + (ks >> 2) * (kNetBytes / 2) + (ks & 3) * 32;
-                    umma_f16(tmem + net * kHid, umma_desc(sA_u + off), umma_desc(sW2_u + off), ks > 0 ? 1u : 0u);
+                    umma_f16(tmem + buf * kHid2 + net * kHid, umma_desc(sA_u + off), umma_desc(sW2_u + off), ks > 0 ? 1u : 0u);
                 }
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_u) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_u + 8 * buf) : "memory");
         }
-        {
-            uint32_t done = 0, spins = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}\n"
-                    : "=r"(done) : "r"(bar_u), "r"(phase) : "memory");
-                if (!done && ++spins > (1u << 26)) __trap();      // a lost MMA completion must not hang the GPU
-            }
-            phase ^= 1u;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-
-        // ------------------------------------------------------------------ heads: TMEM quadrant (warp & 3), 64-column group (warp >> 2)
-        {
-            const int qd = warp & 3, grp = warp >> 2, net = grp >> 1, half = grp & 1;
-            const int row_l = 32 * qd + lane;
-            const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(net * kHid + half * 64);
-            if (net == 0) {
-                float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    float v[16];
-                    tmem_ld16(taddr + cc * 16, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = half * 64 + cc * 16 + i;
-                        const float h = activate<ACT>(v[i] + sS->b2[c]);
-                        const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
-                        const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
-                        pa[0] = fmaf(h, wlo.x, pa[0]); pa[1] = fmaf(h, wlo.y, pa[1]);
-                        pa[2] = fmaf(h, wlo.z, pa[2]); pa[3] = fmaf(h, wlo.w, pa[3]);
-                        pa[4] = fmaf(h, whi.x, pa[4]); pa[5] = fmaf(h, whi.y, pa[5]);
-                        pa[6] = fmaf(h, whi.z, pa[6]); pa[7] = fmaf(h, whi.w, pa[7]);
-                    }
-                }
-                float4 *o = reinterpret_cast<float4 *>(hpA + (row_l * 2 + half) * 8);
-                o[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-                o[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
-            } else {
-                float pc = 0.f;
-#pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    float v[16];
-                    tmem_ld16(taddr + cc * 16, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = half * 64 + cc * 16 + i;
-                        pc = fmaf(activate<ACT>(v[i] + sS->b2[kHid + c]), sS->cw[c], pc);
-                    }
-                }
-                hpC[row_l * 2 + half] = pc;
-            }
-        }
+        if (prev >= 0) do_heads(buf ^ 1);
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
-
-        // ------------------------------------------------------------------ finish the row: logits, value, categorical draw
-        if (tid < kTileM) {
-            const long long row = (long long)tile * kTileM + tid;
-            if (row < p.M) {
-                const int A = p.A;
-                float lg[OC_POLICY_MAX_ACTIONS];
-#pragma unroll
-                for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
-                    lg[a] = hpA[(tid * 2) * 8 + a] + hpA[(tid * 2 + 1) * 8 + a] + sS->b3[a];
-                if (p.logits) {
-#pragma unroll
-                    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
-                        if (a < A) p.logits[row * A + a] = lg[a];
-                }
-                if (p.value) p.value[row] = hpC[tid * 2] + hpC[tid * 2 + 1] + sS->b3c;
-                if (p.key) {
-                    int arg;
-                    float lp;
-                    sample_row(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(p.M * A), row, A, lg, arg, lp);
-                    if (p.action) p.action[row] = arg;
-                    if (p.log_prob) p.log_prob[row] = lp;
-                }
-            }
-        }
+        if (prev >= 0) do_finish(prev);
+        prev = tile;
+    }
+    if (prev >= 0) {              // drain: the last tile's accumulators are in buffer buf ^ 1
+        if (buf) { mbar_wait(bar_u, phase0); } else { mbar_wait(bar_u + 8, phase1); }
+        do_heads(buf ^ 1);
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        do_finish(prev);
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTmemCols) : "memory");
@@ -435,7 +642,7 @@ struct PackArgs {
     const float *kernel[6];
     const float *bias[6];
     const uint8_t *tmpl;
-    float *w1;
+    __half *w1;
     uint8_t *w2img;
     PolicySmall *small;
     int K, A;
@@ -447,7 +654,7 @@ __global__ void oc_policy_pack_kernel(const PackArgs a) {
     // layer 1: [K][actor 128 | critic 128]
     for (long long i = gtid; i < (long long)a.K * kHid2; i += gstride) {
         const int k = (int)(i / kHid2), j = (int)(i % kHid2);
-        a.w1[i] = j < kHid ? a.kernel[0][(size_t)k * kHid + j] : a.kernel[3][(size_t)k * kHid + (j - kHid)];
+        a.w1[i] = __float2half_rn(j < kHid ? a.kernel[0][(size_t)k * kHid + j] : a.kernel[3][(size_t)k * kHid + (j - kHid)]);
     }
     // layer 2: B[n][k] = kernel[k][n] as fp16 in the swizzled K-major image
     __half *img = reinterpret_cast<__half *>(a.w2img);
@@ -480,6 +687,39 @@ __global__ void oc_policy_pack_kernel(const PackArgs a) {
     }
 }
 
+// Layer-1 contribution of every (cell, code): sum_ch (record[code][ch] - template[cell][ch]) * W1[cell*26 + ch, :] in fp32
+// from the fp32 kernels, rounded once to fp16 (records are "as the viewer sees them": agent_1's rows look an agent cell up
+// with the viewer bit of its code flipped).  One CTA per table row, one thread per hidden unit.
+// Rows C*68 and C*68 + 1: zeros (padding entry) and the urgency plane (channel 25 of every cell).
+__global__ void oc_policy_embed_kernel(const float *__restrict__ k_actor, const float *__restrict__ k_critic,
+                                       const uint8_t *__restrict__ tmpl, const DevLayout *__restrict__ L, int C, __half *emb) {
+    const int row = blockIdx.x, j = threadIdx.x;
+    const float *kern = j < kHid ? k_actor : k_critic;
+    const int jj = j < kHid ? j : j - kHid;
+    const int n_rows = C * OC_NUM_CELL_CODES;
+    float s = 0.f;
+    if (row < n_rows) {
+        const int cell = row / OC_NUM_CELL_CODES, code = row % OC_NUM_CELL_CODES;
+        for (int ch = 0; ch < OC_OBS_CHANNELS; ++ch) {
+            const int rv = (int)((L->rec[code][ch >> 2] >> (8 * (ch & 3))) & 255u);
+            const int d = rv - (int)tmpl[cell * OC_OBS_CHANNELS + ch];
+            if (d) s = fmaf((float)d, kern[(size_t)(cell * OC_OBS_CHANNELS + ch) * kHid + jj], s);
+        }
+    } else if (row == n_rows + 1) {
+        for (int cell = 0; cell < C; ++cell) s += kern[(size_t)(cell * OC_OBS_CHANNELS + 25) * kHid + jj];
+    }
+    emb[(size_t)row * kHid2 + j] = __float2half_rn(s);
+}
+
+typedef void (*pol_kernel_t)(const PParams);
+
+// PL = 16-byte pieces per lane and row: 2 covers K <= 994, 4 K <= 2018, 8 K <= 4066 (a 12 x 13 grid)
+pol_kernel_t pick_kernel(int act, int pl) {
+    if (pl == 0) return act == OC_ACT_RELU ? oc_policy_kernel<OC_ACT_RELU, 0> : oc_policy_kernel<OC_ACT_TANH, 0>;
+    if (act == OC_ACT_RELU) return pl == 2 ? oc_policy_kernel<OC_ACT_RELU, 2> : pl == 4 ? oc_policy_kernel<OC_ACT_RELU, 4> : oc_policy_kernel<OC_ACT_RELU, 8>;
+    return pl == 2 ? oc_policy_kernel<OC_ACT_TANH, 2> : pl == 4 ? oc_policy_kernel<OC_ACT_TANH, 4> : oc_policy_kernel<OC_ACT_TANH, 8>;
+}
+
 int gcd16(int k) {
     int g = 16;
     while (k % g) g >>= 1;
@@ -493,10 +733,15 @@ struct oc_policy {
     int nvar, gshift, tv_stride;
     int num_sms;
     size_t smem_bytes;
-    float *w1;
+    __half *w1;
     uint8_t *w2img;
     PolicySmall *small;
     uint8_t *tmpl;
+    int pl;
+    // compact-observation source (desc->layout given)
+    const oc_layout *layout;
+    __half *emb;
+    uint8_t *scan_cells;
 };
 
 extern "C" {
@@ -510,12 +755,15 @@ static int policy_pack(oc_policy *p, const oc_policy_desc *d, cudaStream_t strea
     }
     a.tmpl = p->tmpl; a.w1 = p->w1; a.w2img = p->w2img; a.small = p->small; a.K = p->K; a.A = p->A;
     oc_policy_pack_kernel<<<p->num_sms * 2, 256, 0, stream>>>(a);
+    if (p->layout)
+        oc_policy_embed_kernel<<<p->layout->host.C * OC_NUM_CELL_CODES + 2, kHid2, 0, stream>>>(
+            d->kernel[0], d->kernel[3], p->tmpl, p->layout->dev, p->layout->host.C, p->emb);
     return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
 }
 
 void oc_policy_destroy(oc_policy *p) {
     if (!p) return;
-    cudaFree(p->w1); cudaFree(p->w2img); cudaFree(p->small); cudaFree(p->tmpl);
+    cudaFree(p->w1); cudaFree(p->w2img); cudaFree(p->small); cudaFree(p->tmpl); cudaFree(p->emb); cudaFree(p->scan_cells);
     delete p;
 }
 
@@ -537,20 +785,41 @@ int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
     const int g = gcd16(p->K);
     p->gshift = g == 16 ? 4 : g == 8 ? 3 : g == 4 ? 2 : g == 2 ? 1 : 0;
     p->nvar = 16 / g;
-    p->tv_stride = ((p->K + 30) / 16) * 16;
+    p->tv_stride = ((p->K + 15 + 31) / 16) * 16;     // a + K bytes of template, read in whole 16-byte pieces
     p->smem_bytes = (size_t)kOffTmpl + (size_t)p->nvar * p->tv_stride + 1024;
-    if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return OC_ERR_UNSUPPORTED_LAYOUT; }
-    if (cudaMalloc(&p->w1, (size_t)p->K * kHid2 * sizeof(float)) != cudaSuccess ||
+    const int groups = (((p->K + 30) >> 4) + 31) / 32;
+    p->pl = groups <= 2 ? 2 : groups <= 4 ? 4 : 8;
+    if (groups > 8 || p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return OC_ERR_UNSUPPORTED_LAYOUT; }
+    if (cudaMalloc(&p->w1, (size_t)p->K * kHid2 * sizeof(__half)) != cudaSuccess ||
         cudaMalloc(&p->w2img, 2 * kNetBytes) != cudaSuccess || cudaMalloc(&p->small, sizeof(PolicySmall)) != cudaSuccess ||
         cudaMalloc(&p->tmpl, p->K) != cudaSuccess) {
         oc_policy_destroy(p);
         return OC_ERR_CUDA;
     }
-    cudaError_t e = d->obs_template ? cudaMemcpy(p->tmpl, d->obs_template, p->K, cudaMemcpyHostToDevice)
-                                    : cudaMemset(p->tmpl, 0, p->K);
+    const uint8_t *tmpl_src = d->obs_template;
+    if (d->layout) {      // the env's own static image, and the (view, cell, code) embedding table for oc_policy_forward_cells
+        const oc_layout *lay = d->layout;
+        if (lay->host.C * OC_OBS_CHANNELS != p->K) { oc_policy_destroy(p); return OC_ERR_INVALID_ARG; }
+        tmpl_src = lay->host.obs_tmpl;
+        if (lay->cell_stride <= 64) {
+            uint8_t sc[64] = {0};
+            for (int i = 0; i < lay->host.n_scan; ++i) sc[i] = (uint8_t)(lay->host.scan[i] >> 16);
+            if (cudaMalloc(&p->emb, ((size_t)lay->host.C * OC_NUM_CELL_CODES + 2) * kHid2 * sizeof(__half)) != cudaSuccess ||
+                cudaMalloc(&p->scan_cells, 64) != cudaSuccess ||
+                cudaMemcpy(p->scan_cells, sc, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
+                oc_policy_destroy(p);
+                return OC_ERR_CUDA;
+            }
+            p->layout = lay;
+            if (cudaFuncSetAttribute(pick_kernel(p->act, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
+                oc_policy_destroy(p);
+                return OC_ERR_CUDA;
+            }
+        }
+    }
+    cudaError_t e = tmpl_src ? cudaMemcpy(p->tmpl, tmpl_src, p->K, cudaMemcpyHostToDevice) : cudaMemset(p->tmpl, 0, p->K);
     if (e != cudaSuccess ||
-        cudaFuncSetAttribute(oc_policy_kernel<OC_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(oc_policy_kernel<OC_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
+        cudaFuncSetAttribute(pick_kernel(p->act, p->pl), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
         oc_policy_destroy(p);
         return OC_ERR_CUDA;
     }
@@ -589,8 +858,33 @@ int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (p->act == OC_ACT_RELU) oc_policy_kernel<OC_ACT_RELU><<<grid, kPolThreads, p->smem_bytes, stream>>>(k);
-    else oc_policy_kernel<OC_ACT_TANH><<<grid, kPolThreads, p->smem_bytes, stream>>>(k);
+    pick_kernel(p->act, p->pl)<<<grid, kPolThreads, p->smem_bytes, stream>>>(k);
+    return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+}
+
+int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells, float *logits, float *value,
+                             const uint32_t *key, int32_t *action, float *log_prob, void *stream_) {
+    if (!p || N < 0 || !cells) return OC_ERR_INVALID_ARG;
+    if (!p->layout) return OC_ERR_UNSUPPORTED_LAYOUT;      // created without a layout, or its compact form is too wide
+    if ((action || log_prob) && !key) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    const int64_t M = 2 * N;
+    if (M * p->A > 0x7fffffffll) return OC_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(key) |
+         reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(log_prob)) & 3u)
+        return OC_ERR_ALIGNMENT;
+    PParams k;
+    std::memset(&k, 0, sizeof(k));
+    k.w1 = p->w1; k.w2img = p->w2img; k.small = p->small; k.tmpl = p->tmpl;
+    k.M = M; k.N = N; k.K = p->K; k.A = p->A; k.part = p->part;
+    k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
+    k.n_tiles = (int)((M + kTileM - 1) / kTileM);
+    k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
+    k.cells = cells; k.emb = p->emb; k.scan_cells = p->scan_cells;
+    k.cell_stride = p->layout->cell_stride; k.cell_agents = p->layout->cell_agents; k.n_scan = p->layout->host.n_scan;
+    k.C = p->layout->host.C;
+    const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
+    pick_kernel(p->act, 0)<<<grid, kPolThreads, p->smem_bytes, static_cast<cudaStream_t>(stream_)>>>(k);
     return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
 }
 
@@ -600,7 +894,7 @@ int oc_policy_sample(int prng_mode, int64_t M, int32_t A, const float *logits, c
         (prng_mode != OC_PRNG_THREEFRY_LEGACY && prng_mode != OC_PRNG_THREEFRY_PARTITIONABLE) || M * A > 0x7fffffffll)
         return OC_ERR_INVALID_ARG;
     if (M == 0) return OC_OK;
-    oc_policy_sample_kernel<<<(unsigned)((M + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    oc_policy_sample_kernel<<<(unsigned)((4 * M + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         prng_mode, M, A, logits, key, action, log_prob);
     return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
 }

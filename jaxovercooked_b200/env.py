@@ -240,8 +240,13 @@ class Overcooked:
         else:
             obs0, obs1, reward, sh0, sh1, done = (out[k] for k in ("obs0", "obs1", "reward", "shaped0", "shaped1", "done"))
         ex = None
-        if log is not None or stats is not None or lazy is not None:
+        cells = out.get("cells") if out is not None else None
+        if log is not None or stats is not None or lazy is not None or cells is not None:
             e = _lib.StepExtras()
+            if cells is not None:
+                if cells.dtype != torch.uint8 or tuple(cells.shape) != tuple(batch) + (self.info.cell_stride,) or not cells.is_contiguous():
+                    raise ValueError(f"out['cells'] must be a contiguous uint8 tensor of shape {tuple(batch) + (self.info.cell_stride,)}")
+                e.cells = cells.data_ptr()
             if lazy is not None:
                 e.split_key, e.split_num, e.split_first = lazy.key.data_ptr(), lazy.num, lazy.first
             if log is not None:
@@ -268,15 +273,27 @@ class Overcooked:
         Everything is enqueued on `stream` (default: a new stream), so several batches overlap copy and compute."""
         return HostStepper(self, state, n_global, first, stream)
 
-    def get_obs(self, state):
-        """overcooked.py:250-364."""
+    def get_obs(self, state, cells=None):
+        """overcooked.py:250-364.  `cells` (uint8 [N, cell_stride]) also receives the compact form."""
         batch = tuple(state.time.shape)
         n = int(np.prod(batch)) if batch else 1
         obs0, obs1 = self._obs_buffers(batch)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.oc_get_obs(self._handle, n, self._state_ptrs(state, batch), obs0.data_ptr(),
-                                            obs1.data_ptr(), self._stream()), "oc_get_obs")
+            _lib.check(self._lib.oc_get_obs_cells(self._handle, n, self._state_ptrs(state, batch), obs0.data_ptr(),
+                                                  obs1.data_ptr(), cells.data_ptr() if cells is not None else None,
+                                                  self._stream()), "oc_get_obs")
         return {"agent_0": obs0, "agent_1": obs1}
+
+    def empty_cells(self, n):
+        """Buffer for the compact observations of `n` environments (see include/oc_b200.h, oc_step_extras.cells)."""
+        return torch.full((n, self.info.cell_stride), 255, dtype=torch.uint8, device=self.device)
+
+    def cell_tables(self):
+        """(records uint8[68, 26], scan_cells int32[n_scan]): how to expand the compact form back into observations."""
+        rec = np.zeros((68, 26), np.uint8)
+        sc = np.zeros((self.info.n_scan,), np.int32)
+        _lib.check(self._lib.oc_layout_cell_tables(self._handle, rec.ctypes.data, sc.ctypes.data), "oc_layout_cell_tables")
+        return rec, sc
 
     def _action(self, a, batch):
         if not torch.is_tensor(a):

@@ -87,7 +87,7 @@ class ActorCritic:
         return {"params": {k: {n: torch.as_tensor(np.asarray(v[n], np.float32)).contiguous().to(device) for n in ("kernel", "bias")}
                            for k, v in params["params"].items()}}
 
-    def _desc(self, p, obs_dim, template):
+    def _desc(self, p, obs_dim, template, layout=None):
         d = _lib.PolicyDesc()
         d.obs_dim, d.action_dim = obs_dim, self.action_dim
         d.activation = 1 if self.activation == "relu" else 0
@@ -102,26 +102,32 @@ class ActorCritic:
                 raise ValueError(f"{name}: parameters must be contiguous float32 CUDA tensors")
             d.kernel[i], d.bias[i] = k.data_ptr(), b.data_ptr()
         d.obs_template = template.ctypes.data if template is not None else None
+        d.layout = layout
         return d
 
-    def bind(self, params, obs_template=None):
-        """Pack `params` for the kernels (done implicitly by apply/act; call it to pass an `obs_template`)."""
+    def bind(self, params, obs_template=None, env=None):
+        """Pack `params` for the kernels (done implicitly by apply/act).  `obs_template` (uint8, obs_dim bytes) lets
+        layer 1 be evaluated relative to an observation most rows are close to; `env` (an `Overcooked`) uses the env's own
+        static image for that and additionally enables `act_cells` / `apply_cells` on the env's compact observations."""
         p = params["params"]
         obs_dim = int(p["Dense_0"]["kernel"].shape[0])
         tmpl = None
-        if obs_template is not None:
+        if env is not None:
+            if env.height * env.width * 26 != obs_dim:
+                raise ValueError(f"the env's observations have {env.height * env.width * 26} bytes, the network reads {obs_dim}")
+        elif obs_template is not None:
             tmpl = np.ascontiguousarray(np.asarray(obs_template, np.uint8).reshape(-1))
             if tmpl.size != obs_dim:
                 raise ValueError(f"obs_template has {tmpl.size} bytes, the network reads {obs_dim}")
         old = self._bound.pop(id(p), None)
         if old is not None:
             self._lib.oc_policy_destroy(old[0])
-        d = self._desc(p, obs_dim, tmpl)
+        d = self._desc(p, obs_dim, tmpl, env._handle if env is not None else None)
         h = C.c_void_p()
         with torch.cuda.device(p["Dense_0"]["kernel"].device):
             torch.cuda.current_stream().synchronize()          # the parameters may still be being written
             _lib.check(self._lib.oc_policy_create(C.byref(d), C.byref(h)), "oc_policy_create")
-        self._bound[id(p)] = [h, self._versions(p), (p, tmpl), obs_dim]
+        self._bound[id(p)] = [h, self._versions(p), (p, tmpl, env), obs_dim]
         return self
 
     @staticmethod
@@ -136,7 +142,7 @@ class ActorCritic:
             ent = self._bound[id(p)]
         v = self._versions(p)
         if v != ent[1]:                                          # an optimiser step happened: repack on this stream
-            d = self._desc(p, ent[3], None)
+            d = self._desc(p, ent[3], None, ent[2][2]._handle if ent[2][2] is not None else None)
             _lib.check(self._lib.oc_policy_update(ent[0], C.byref(d), torch.cuda.current_stream().cuda_stream), "oc_policy_update")
             ent[1] = v
         return ent[0]
@@ -175,6 +181,37 @@ class ActorCritic:
             _lib.check(self._lib.oc_policy_forward(h, M, x.data_ptr(), ptr(logits), ptr(value), kp, ptr(action), ptr(log_prob),
                                                    torch.cuda.current_stream().cuda_stream), "oc_policy_forward")
         return logits, value, action, log_prob
+
+    def _forward_cells(self, params, cells, key, want_logits=True, out=None):
+        h = self._handle(params)
+        if cells.dtype != torch.uint8 or not cells.is_cuda or cells.dim() != 2 or not cells.is_contiguous():
+            raise ValueError("cells must be a contiguous uint8 CUDA tensor [N, cell_stride] (env.empty_cells / out['cells'])")
+        N, dev = cells.shape[0], cells.device
+        M = 2 * N
+        out = out or {}
+        logits = out.get("logits") if "logits" in out else (torch.empty((M, self.action_dim), dtype=torch.float32, device=dev) if want_logits else None)
+        value = out.get("value") if "value" in out else torch.empty((M,), dtype=torch.float32, device=dev)
+        action = log_prob = kp = None
+        if key is not None:
+            key = key if key.dtype == torch.uint32 else key.to(torch.uint32)
+            action = out.get("action") if "action" in out else torch.empty((M,), dtype=torch.int32, device=dev)
+            log_prob = out.get("log_prob") if "log_prob" in out else torch.empty((M,), dtype=torch.float32, device=dev)
+            kp = key.data_ptr()
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.oc_policy_forward_cells(h, N, cells.data_ptr(), ptr(logits), ptr(value), kp, ptr(action),
+                                                         ptr(log_prob), torch.cuda.current_stream().cuda_stream), "oc_policy_forward_cells")
+        return logits, value, action, log_prob
+
+    def apply_cells(self, params, cells):
+        """`apply` on the env's compact observations: rows [0, N) agent_0, [N, 2N) agent_1 (the batchify order)."""
+        logits, value, _, _ = self._forward_cells(params, cells, None)
+        return Categorical(logits, self.prng_mode), value
+
+    def act_cells(self, params, cells, rng, *, out=None, want_logits=False):
+        """`act` on the env's compact observations (needs `bind(params, env=env)`); the 26-channel images are not read."""
+        logits, value, action, log_prob = self._forward_cells(params, cells, rng, want_logits=want_logits, out=out)
+        return (action, log_prob, value, logits) if want_logits else (action, log_prob, value)
 
     def apply(self, params, x):
         """`pi, value = network.apply(params, obs_batch)`."""

@@ -157,3 +157,103 @@ def test_errors():
     bad["params"]["Dense_1"] = {"kernel": torch.zeros((128, 64), device="cuda"), "bias": torch.zeros(64, device="cuda")}
     with pytest.raises(ValueError):
         net.apply(bad, torch.zeros((4, 520), dtype=torch.uint8, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ compact observations
+
+def expand_cells(env, cells):
+    """Rebuild both agents' observations from the compact form with the layout's decoding tables (pure NumPy)."""
+    rec, scan_cells = env.cell_tables()
+    info = env.info
+    tmpl = env.obs_template().reshape(-1, 26)
+    n = cells.shape[0]
+    obs = [np.tile(tmpl, (n, 1, 1)), np.tile(tmpl, (n, 1, 1))]
+    for e in range(n):
+        row = cells[e]
+        for s in range(info.n_scan):
+            if row[s] != 255:
+                obs[0][e, scan_cells[s]] = rec[row[s]]
+                obs[1][e, scan_cells[s]] = rec[row[s]]
+        for a in range(2):
+            cell, code = row[info.cell_agents + 2 * a], row[info.cell_agents + 2 * a + 1]
+            obs[0][e, cell] = rec[code]
+            obs[1][e, cell] = rec[35 + ((code - 35) ^ 16)]
+        if row[info.cell_agents + 4]:
+            obs[0][e, :, 25] = 1
+            obs[1][e, :, 25] = 1
+    shape = (n, env.height, env.width, 26)
+    return obs[0].reshape(shape), obs[1].reshape(shape)
+
+
+@pytest.mark.parametrize("layout,padded,random_reset", [("cramped_room", False, False), ("coord_ring", True, False),
+                                                        ("bottleneck_large", False, True), ("forced_coord", False, True)])
+def test_cells_are_the_observations(layout, padded, random_reset):
+    """BIT-EXACT: expanding the compact observations reproduces obs0 / obs1 of the same step, across interactions,
+    the urgency window and auto-resets (max_steps = 45 so that both happen within the run)."""
+    lay = ocb.cl_sequence_padded()[layout] if padded else ocb.overcooked_layouts[layout]
+    env = ocb.make("overcooked", layout=lay, random_reset=random_reset, max_steps=45)
+    n = 67
+    rng = jr.PRNGKey(3)
+    rng, sub = jr.split(rng)
+    obs, state = env.reset(jr.split(sub, n))
+    cells = env.empty_cells(n)
+    obs = env.get_obs(state, cells=cells)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(100):
+        o0, o1 = expand_cells(env, cells.cpu().numpy())
+        np.testing.assert_array_equal(o0, obs["agent_0"].cpu().numpy(), err_msg=f"step {t} agent_0")
+        np.testing.assert_array_equal(o1, obs["agent_1"].cpu().numpy(), err_msg=f"step {t} agent_1")
+        rng, sub = jr.split(rng)
+        acts = {a: torch.randint(0, 6, (n,), dtype=torch.int32, device="cuda", generator=g) for a in ("agent_0", "agent_1")}
+        # interact more often than uniformly, so that pots fill and loose items appear
+        for a in acts:
+            acts[a][torch.rand(n, device="cuda", generator=g) < 0.3] = 5
+        out = {"obs0": torch.empty_like(obs["agent_0"]), "obs1": torch.empty_like(obs["agent_1"]),
+               "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
+               "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"), "cells": cells}
+        obs, state, *_ = env.step(jr.split(sub, n), state, acts, out=out)
+    assert int((cells[:, : env.info.n_scan] != 255).sum()) > 0, "no scan cell ever deviated: the test did not exercise them"
+
+
+@pytest.mark.parametrize("layout,padded", [("cramped_room", False), ("coord_ring", True), ("bottleneck_large", False)])
+def test_forward_cells_matches_forward_on_observations(layout, padded):
+    lay = ocb.cl_sequence_padded()[layout] if padded else ocb.overcooked_layouts[layout]
+    env = ocb.make("overcooked", layout=lay, max_steps=60)
+    K = env.height * env.width * 26
+    n = 517
+    net = ActorCritic(6)
+    params = po.make_params(77, K)
+    params["params"]["Dense_2"]["kernel"] = (params["params"]["Dense_2"]["kernel"] * np.float32(300)).astype(np.float32)
+    P = net.params_from_numpy(params)
+    net.bind(P, env=env)
+    rng = jr.PRNGKey(9)
+    rng, sub = jr.split(rng)
+    obs, state = env.reset(jr.split(sub, n))
+    cells = env.empty_cells(n)
+    obs = env.get_obs(state, cells=cells)
+    worst = 0.0
+    for t in range(70):
+        rng, k_act, k_step = jr.split(rng, 3)
+        action, log_prob, value, logits = net.act_cells(P, cells, k_act, want_logits=True)
+        batch = torch.cat([obs["agent_0"].reshape(n, -1), obs["agent_1"].reshape(n, -1)], dim=0)
+        lo, vo = po.forward(params, batch.cpu().numpy())
+        check_outputs(logits.cpu().numpy(), value.cpu().numpy(), lo, vo, f"{layout} step {t} (cells)")
+        # the observation-scanning path sees the same rows
+        a2, lp2, v2, l2 = net.act(P, batch, k_act, want_logits=True)
+        worst = max(worst, float((l2 - logits).abs().max()), float((v2 - value).abs().max()))
+        # same logits -> same draw: compare where the two paths' logits agree to the last bit
+        same = (l2 == logits).all(dim=1)
+        assert torch.equal(a2[same], action[same])
+        out = {"obs0": torch.empty_like(obs["agent_0"]), "obs1": torch.empty_like(obs["agent_1"]),
+               "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
+               "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"), "cells": cells}
+        obs, state, *_ = env.step(jr.split(k_step, n), state, {"agent_0": action[:n], "agent_1": action[n:]}, out=out)
+    print(f"{layout}: max |cells path - obs path| = {worst:.2e}")
+    assert worst < 2e-2
+
+
+def test_forward_cells_needs_a_layout():
+    net = ActorCritic(6)
+    P = net.params_from_numpy(po.make_params(1, 520))
+    with pytest.raises(ocb._lib.OcError):
+        net.act_cells(P, torch.zeros((4, 16), dtype=torch.uint8, device="cuda"), jr.PRNGKey(0))
