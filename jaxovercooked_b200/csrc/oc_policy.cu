@@ -37,8 +37,8 @@ namespace {
 constexpr int kHid = OC_POLICY_HIDDEN;        // 128
 constexpr int kHid2 = 2 * kHid;               // actor | critic
 constexpr int kTileM = 128;
-constexpr int kPolWarps = 16;
-constexpr int kPolThreads = kPolWarps * 32;
+constexpr int kObsWarps = 16;                 // warps per CTA when rows are uint8 observations (register-hungry scan)
+constexpr int kCellWarps = 32;                // ... and when rows are compact observations (more warps hide the gather latency)
 constexpr int kListCap = 512;                 // (k, delta) entries per warp between two flushes
 constexpr int kListWords = kListCap + 8;      // + padding to a multiple of 8 entries
 constexpr int kNetBytes = kTileM * kHid * 2;  // one fp16 128x128 operand image: 32 KB = 2 swizzle atoms of 16 KB
@@ -60,11 +60,11 @@ constexpr int kOffA = 0;
 constexpr int kOffW2 = kOffA + 2 * kNetBytes;
 constexpr int kOffSmall = kOffW2 + 2 * kNetBytes;
 constexpr int kOffHpA = kOffSmall + (int)sizeof(PolicySmall);
-constexpr int kOffHpC = kOffHpA + kTileM * 2 * 8 * 4;
-constexpr int kOffList = kOffHpC + kTileM * 2 * 4;
-constexpr int kOffMask = kOffList + kPolWarps * kListWords * 4;
+constexpr int kOffHpC = kOffHpA + kTileM * 8 * 8 * 4;      // head partials: up to 8 column slices
+constexpr int kOffList = kOffHpC + kTileM * 8 * 4;
+constexpr int kOffMask = kOffList + kObsWarps * kListWords * 4;
 constexpr int kOffBar = kOffMask + 16 * 2 * 16;
-constexpr int kOffTmpl = kOffBar + 32;
+constexpr int kOffTmpl = kOffBar + 48;      // two accumulator barriers, the TMEM base address, the W2 barrier
 static_assert(kOffHpA % 16 == 0 && kOffList % 16 == 0 && kOffMask % 16 == 0 && kOffTmpl % 16 == 0, "alignment");
 
 struct PParams {
@@ -137,7 +137,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // Categorical(logits).sample(seed=key) and .log_prob(action) for one row (distrax over jax.random.categorical):
 // action = argmax_a(logits[a] + gumbel(key, (1, M, A))[0, row, a]), first maximum wins; log_prob = log_softmax(logits)[action]
-// Four consecutive lanes share a row: lane part `s` draws the noise of actions s and s + 4, a 4-lane butterfly picks the winner.
+// A few consecutive lanes share a row: each draws the noise of its actions, a butterfly over those lanes picks the winner.
 __device__ __forceinline__ float gumbel_at(int part, uint32_t k0, uint32_t k1, int n, int j) {
     // jax.random.gumbel: -log(-log(uniform(key, shape, minval=tiny, maxval=1)))
     const uint32_t bits = bits_at(part, k0, k1, n, j);
@@ -146,34 +146,41 @@ __device__ __forceinline__ float gumbel_at(int part, uint32_t k0, uint32_t k1, i
     return -logf(-logf(u));
 }
 
-__device__ __forceinline__ void sample_row4(int part, uint32_t k0, uint32_t k1, int n, long long row, int A, int s,
-                                            const float (&lg)[OC_POLICY_MAX_ACTIONS], int &arg, float &lp) {
-    float best = -INFINITY;
+// TPR consecutive lanes share a row (4 or 8); lane part `s` owns the logits of actions s, s + TPR, ... in l[]: it draws their
+// noise, butterflies over the TPR lanes pick the winner and form the log-sum-exp.
+template <int TPR>
+__device__ __forceinline__ void sample_lanes(int part, uint32_t k0, uint32_t k1, int n, long long row, int A, int s,
+                                             const float (&l)[OC_POLICY_MAX_ACTIONS / TPR], int &arg, float &lp) {
+    constexpr int NA = OC_POLICY_MAX_ACTIONS / TPR;
+    float best = -INFINITY, mx = -INFINITY;
     arg = OC_POLICY_MAX_ACTIONS;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int a = s + 4 * h;
+    for (int h = 0; h < NA; ++h) {
+        const int a = s + TPR * h;
         if (a < A) {
-            float l = 0.f;
-#pragma unroll
-            for (int q = 0; q < OC_POLICY_MAX_ACTIONS; ++q) if (q == a) l = lg[q];
-            const float z = l + gumbel_at(part, k0, k1, n, (int)(row * A + a));
+            mx = fmaxf(mx, l[h]);
+            const float z = l[h] + gumbel_at(part, k0, k1, n, (int)(row * A + a));
             if (arg == OC_POLICY_MAX_ACTIONS || z > best) { best = z; arg = a; }
         }
     }
 #pragma unroll
-    for (int d = 1; d < 4; d <<= 1) {
+    for (int d = 1; d < TPR; d <<= 1) {
         const float zo = __shfl_xor_sync(0xffffffffu, best, d);
         const int ao = __shfl_xor_sync(0xffffffffu, arg, d);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
         if (ao < OC_POLICY_MAX_ACTIONS && (arg == OC_POLICY_MAX_ACTIONS || zo > best || (zo == best && ao < arg))) { best = zo; arg = ao; }
     }
-    float mx = lg[0];
-#pragma unroll
-    for (int q = 1; q < OC_POLICY_MAX_ACTIONS; ++q) if (q < A) mx = fmaxf(mx, lg[q]);
     float sum = 0.f, la = 0.f;
 #pragma unroll
-    for (int q = 0; q < OC_POLICY_MAX_ACTIONS; ++q)
-        if (q < A) { sum += expf(lg[q] - mx); if (q == arg) la = lg[q]; }
+    for (int h = 0; h < NA; ++h) {
+        const int a = s + TPR * h;
+        if (a < A) { sum += expf(l[h] - mx); if (a == arg) la = l[h]; }
+    }
+#pragma unroll
+    for (int d = 1; d < TPR; d <<= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        la += __shfl_xor_sync(0xffffffffu, la, d);
+    }
     lp = la - (mx + logf(sum));
 }
 
@@ -181,14 +188,15 @@ __global__ void oc_policy_sample_kernel(int part, long long M, int A, const floa
                                         const uint32_t *__restrict__ key, int32_t *action, float *log_prob) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long row = t >> 2;
+    const int s = (int)(t & 3);
     const bool live = row < M;
-    float lg[OC_POLICY_MAX_ACTIONS];
+    float l[2];
 #pragma unroll
-    for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a) lg[a] = (live && a < A) ? logits[row * A + a] : 0.f;
+    for (int h = 0; h < 2; ++h) l[h] = (live && s + 4 * h < A) ? logits[row * A + s + 4 * h] : 0.f;
     int arg;
     float lp;
-    sample_row4(part, __ldg(key), __ldg(key + 1), (int)(M * A), live ? row : 0, A, (int)(t & 3), lg, arg, lp);
-    if (live && (t & 3) == 0) {
+    sample_lanes<4>(part, __ldg(key), __ldg(key + 1), (int)(M * A), live ? row : 0, A, s, l, arg, lp);
+    if (live && s == 0) {
         if (action) action[row] = arg;
         if (log_prob) log_prob[row] = lp;
     }
@@ -260,21 +268,28 @@ __device__ __forceinline__ int emit_piece(uint32_t *list, int pos, const uint4 &
     return pos;
 }
 
-// this lane's bytes of one env's compact observation (slots lane and lane + 32)
+// this lane's bytes of one env's compact observation (slots lane and lane + 32); 32-bit arithmetic: 2N * cell_stride < 2^31
 __device__ __forceinline__ void load_cells(const PParams &p, long long tile, int row_l, int lane, uint32_t (&cb)[2]) {
-    const long long row = tile * kTileM + row_l;
-    if (tile < p.n_tiles && row < p.M) {
-        const uint8_t *src = p.cells + (row >= p.N ? row - p.N : row) * p.cell_stride;
-        cb[0] = lane < p.cell_stride ? __ldg(src + lane) : 0xffu;
-        cb[1] = lane + 32 < p.cell_stride ? __ldg(src + lane + 32) : 0xffu;
+    if (tile < p.n_tiles) {
+        const int row = (int)tile * kTileM + row_l, n = (int)p.N;
+        if (row < 2 * n) {
+            const uint8_t *src = p.cells + (unsigned)((row >= n ? row - n : row) * p.cell_stride + lane);
+            cb[0] = lane < p.cell_stride ? __ldg(src) : 0xffu;
+            if (p.cell_stride > 32) cb[1] = lane + 32 < p.cell_stride ? __ldg(src + 32) : 0xffu;
+        }
     }
 }
 
 // PL > 0: rows are uint8 observations, PL 16-byte pieces per lane and row.  PL == 0: rows come from the env kernel's
 // compact observations (cells) and layer 1 is a sum of precomputed (view, cell, code) embeddings.
 template <int ACT, int PL>
-__global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams p) {
+__global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_policy_kernel(const PParams p) {
     constexpr int PLA = PL > 0 ? PL : 1;
+    constexpr int NW = PL > 0 ? kObsWarps : kCellWarps;     // warps per CTA
+    constexpr int kPolThreads = NW * 32;
+    constexpr int RND = kTileM / NW, RSH = NW == 16 ? 3 : 2;  // rows per warp and tile (8 or 4), log2 of it
+    constexpr int NG = NW / 8;                               // 64- or 32-column groups per net in the heads phase (2 or 4)
+    constexpr int TPR = kPolThreads / kTileM;                // threads per row in the finishing phase (4 or 8)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = sm + kOffA;
@@ -292,9 +307,6 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
 
     // ---- one-time setup: resident W2 images, small parameters, template variants, TMEM, mbarrier
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.w2img);
-        uint4 *dst = reinterpret_cast<uint4 *>(sW2);
-        for (int i = tid; i < 2 * kNetBytes / 16; i += kPolThreads) dst[i] = __ldg(src + i);
         const uint4 *s2 = reinterpret_cast<const uint4 *>(p.small);
         uint4 *d2 = reinterpret_cast<uint4 *>(sS);
         for (int i = tid; i < (int)sizeof(PolicySmall) / 16; i += kPolThreads) d2[i] = __ldg(s2 + i);
@@ -315,10 +327,16 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_addr(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
-    if (tid == 32) {
+    if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_addr(mbar)) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_addr(mbar) + 8) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_addr(mbar) + 24) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        // the resident layer-2 weights (two 32 KB fp16 images) arrive through the bulk-copy engine while the first tile's
+        // layer 1 runs; only this thread -- the one that issues the MMAs -- ever waits for them
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(mbar) + 24), "r"(2 * kNetBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(smem_addr(sW2)), "l"(p.w2img), "r"(2 * kNetBytes), "r"(smem_addr(mbar) + 24) : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // W2 image: generic-proxy writes -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -335,10 +353,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
     uint32_t cbA[2] = {0xffu, 0xffu}, cbB[2] = {0xffu, 0xffu};
     if (PL > 0) {
         load_row<PLA>(p, blockIdx.x, warp, lane, pfA);
-        load_row<PLA>(p, blockIdx.x, kPolWarps + warp, lane, pfB);
+        load_row<PLA>(p, blockIdx.x, NW + warp, lane, pfB);
     } else {
         load_cells(p, blockIdx.x, warp, lane, cbA);
-        load_cells(p, blockIdx.x, kPolWarps + warp, lane, cbB);
+        load_cells(p, blockIdx.x, NW + warp, lane, cbB);
     }
     uint8_t *s_sc = reinterpret_cast<uint8_t *>(sm + kOffMask);          // [n_scan] scan slot -> cell (cells source only)
 
@@ -358,10 +376,20 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
         *reinterpret_cast<uint4 *>(dst) = pk;
     };
 
-    // layer 1 of one row from its compact observation: base + sum of the embeddings of the deviating cells
+    // layer 1 of one row from its compact observation: base + sum of the embeddings of the deviating cells.
+    // What a slot means depends only on the lane, so it is decoded once: kind 1 = scan cell (table row sbase + code),
+    // 2 = an agent's code (its cell is in the previous slot), 3 = urgency flag, 0 = padding.
+    int kind[2], sbase[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int slot = g * 32 + lane, ag = slot - p.cell_agents;
+        kind[g] = (PL == 0 && slot < p.n_scan) ? 1 : (ag == 1 || ag == 3) ? 2 : ag == 4 ? 3 : 0;
+        sbase[g] = (PL == 0 && slot < p.n_scan) ? (int)s_sc[slot] * OC_NUM_CELL_CODES : 0;
+    }
+    int *wl = reinterpret_cast<int *>(lists) + warp * 72;        // this warp's compacted table rows (<= 62 + padding)
     auto do_row_cells = [&](uint32_t (&cb)[2], const long long tile, const int rr) {
-        const int row_l = rr * kPolWarps + warp;
-        const long long row = tile * kTileM + row_l;
+        const int row_l = rr * NW + warp;
+        const int row = (int)tile * kTileM + row_l;
         float acc[8];
         {
             const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
@@ -369,64 +397,54 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
             acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
             acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
         }
-        if (row < p.M) {
-            const int view = row >= p.N ? 1 : 0;
+        int cnt = 0;
+        if (row < (int)p.M) {
+            const int flip = row >= (int)p.N ? 16 : 0;        // agent_1's rows see the agent codes with the viewer bit flipped
             const int idx_zero = p.C * OC_NUM_CELL_CODES;
-            int idx[2];
-            unsigned bal[2];
+            const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                const int slot = g * 32 + lane;
+                if (g == 1 && p.cell_stride <= 32) break;      // most layouts: one byte per lane covers the env
                 const int b = (int)cb[g];
                 const int prev = (int)__shfl_up_sync(0xffffffffu, cb[g], 1);     // an agent's cell sits one slot before its code
-                const int ag = slot - p.cell_agents;
-                bool valid = false;
-                int ix = idx_zero;
-                if (slot < p.n_scan) {
-                    valid = b != 0xff;
-                    ix = (int)s_sc[slot] * OC_NUM_CELL_CODES + b;
-                } else if (ag == 1 || ag == 3) {
-                    valid = true;
-                    ix = prev * OC_NUM_CELL_CODES + (view ? kCodeAgent + ((b - kCodeAgent) ^ 16) : b);
-                } else if (ag == 4) {
-                    valid = b != 0;
-                    ix = idx_zero + 1;
-                }
-                idx[g] = ix;
-                bal[g] = __ballot_sync(0xffffffffu, valid);
+                const int ix = kind[g] == 1 ? sbase[g] + b
+                             : kind[g] == 2 ? prev * OC_NUM_CELL_CODES + kCodeAgent + ((b - kCodeAgent) ^ flip)
+                                            : idx_zero + 1;
+                const bool valid = kind[g] == 1 ? b != 0xff : kind[g] == 2 ? true : kind[g] == 3 ? b != 0 : false;
+                const unsigned bal = __ballot_sync(0xffffffffu, valid);
+                if (valid) wl[cnt + __popc(bal & lt)] = ix;      // slot order: the sum below is deterministic
+                cnt += __popc(bal);
             }
-            {   // this slot is free again: fetch the row after next
-                const int it2 = item + 2;
-                load_cells(p, (long long)blockIdx.x + (long long)(it2 >> 3) * gridDim.x, (it2 & 7) * kPolWarps + warp, lane, cb);
-            }
-            const __half *el = p.emb + 8 * lane;
-            while (bal[0] | bal[1]) {                      // four embeddings in flight, in slot order (deterministic sum)
-                uint4 w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int ix = idx_zero;
-                    if (bal[0]) { const int src = __ffs(bal[0]) - 1; bal[0] &= bal[0] - 1; ix = __shfl_sync(0xffffffffu, idx[0], src); }
-                    else if (bal[1]) { const int src = __ffs(bal[1]) - 1; bal[1] &= bal[1] - 1; ix = __shfl_sync(0xffffffffu, idx[1], src); }
-                    w[u] = __ldg(reinterpret_cast<const uint4 *>(el + (size_t)ix * kHid2));
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    fma_h2(acc[0], acc[1], w[u].x, (unsigned short)0x3c00);
-                    fma_h2(acc[2], acc[3], w[u].y, (unsigned short)0x3c00);
-                    fma_h2(acc[4], acc[5], w[u].z, (unsigned short)0x3c00);
-                    fma_h2(acc[6], acc[7], w[u].w, (unsigned short)0x3c00);
-                }
-            }
-        } else {
-            const int it2 = item + 2;
-            load_cells(p, (long long)blockIdx.x + (long long)(it2 >> 3) * gridDim.x, (it2 & 7) * kPolWarps + warp, lane, cb);
+            if (lane < 3) wl[cnt + lane] = idx_zero;             // pad to a multiple of 4 with the zero row
+            __syncwarp();
         }
-        ++item;
+        {   // this slot is free again: fetch the row after next
+            const int it2 = item + 2;
+            load_cells(p, (long long)blockIdx.x + (long long)(it2 >> RSH) * gridDim.x, (it2 & (RND - 1)) * NW + warp, lane, cb);
+            ++item;
+        }
+        const __half *el = p.emb + 8 * lane;
+        for (int i = 0; i < cnt; i += 4) {                       // four embeddings in flight
+            const int4 ix = *reinterpret_cast<const int4 *>(wl + i);
+            uint4 w[4];
+            w[0] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.x * kHid2));
+            w[1] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.y * kHid2));
+            w[2] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.z * kHid2));
+            w[3] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.w * kHid2));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                fma_h2(acc[0], acc[1], w[u].x, (unsigned short)0x3c00);
+                fma_h2(acc[2], acc[3], w[u].y, (unsigned short)0x3c00);
+                fma_h2(acc[4], acc[5], w[u].z, (unsigned short)0x3c00);
+                fma_h2(acc[6], acc[7], w[u].w, (unsigned short)0x3c00);
+            }
+        }
+        __syncwarp();
         finish_row(row_l, acc);
     };
 
     auto do_row = [&](uint4 (&pf)[PLA], const long long tile, const int rr) {
-        const int row_l = rr * kPolWarps + warp;
+        const int row_l = rr * NW + warp;
         float acc[8];
         {
             const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
@@ -491,7 +509,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
         }
         {   // this slot is free again: fetch the row after next
             const int it2 = item + 2;
-            load_row<PLA>(p, (long long)blockIdx.x + (long long)(it2 >> 3) * gridDim.x, (it2 & 7) * kPolWarps + warp, lane, pf);
+            load_row<PLA>(p, (long long)blockIdx.x + (long long)(it2 >> RSH) * gridDim.x, (it2 & (RND - 1)) * NW + warp, lane, pf);
             ++item;
         }
         if (n) gather_rows(p.w1, list, n, lane, acc);
@@ -511,20 +529,21 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     };
     // heads: TMEM quadrant (warp & 3), 64-column group (warp >> 2) of accumulator buffer `buf`
+    // heads: TMEM lane quadrant (warp & 3) x column group (warp >> 2; NG groups of 128/NG columns per net) of accumulator `buf`
     auto do_heads = [&](const int buf) {
-    {
-        const int qd = warp & 3, grp = warp >> 2, net = grp >> 1, half = grp & 1;
+        constexpr int GC = kHid / NG;                        // columns per group
+        const int qd = warp & 3, grp = warp >> 2, net = grp / NG, part = grp % NG;
         const int row_l = 32 * qd + lane;
-        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(buf * kHid2 + net * kHid + half * 64);
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(buf * kHid2 + net * kHid + part * GC);
         if (net == 0) {
             float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < GC / 16; ++cc) {
                 float v[16];
                 tmem_ld16(taddr + cc * 16, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int c = half * 64 + cc * 16 + i;
+                    const int c = part * GC + cc * 16 + i;
                     const float h = activate<ACT>(v[i] + sS->b2[c]);
                     const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
                     const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
@@ -534,59 +553,62 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
                     pa[6] = fmaf(h, whi.z, pa[6]); pa[7] = fmaf(h, whi.w, pa[7]);
                 }
             }
-            float4 *o = reinterpret_cast<float4 *>(hpA + (row_l * 2 + half) * 8);
+            float4 *o = reinterpret_cast<float4 *>(hpA + (row_l * NG + part) * 8);
             o[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
             o[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
         } else {
             float pc = 0.f;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < GC / 16; ++cc) {
                 float v[16];
                 tmem_ld16(taddr + cc * 16, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int c = half * 64 + cc * 16 + i;
+                    const int c = part * GC + cc * 16 + i;
                     pc = fmaf(activate<ACT>(v[i] + sS->b2[kHid + c]), sS->cw[c], pc);
                 }
             }
-            hpC[row_l * 2 + half] = pc;
+            hpC[row_l * NG + part] = pc;
         }
-    }
     };
-    // finish the rows of `tile`: logits, value, categorical draw (4 threads per row)
+    // finish the rows of `tile`: logits, value, categorical draw (TPR threads per row)
     auto do_finish = [&](const long long tile) {
-    {
-        const int row_l = tid >> 2, s4 = tid & 3;
+        constexpr int NA = OC_POLICY_MAX_ACTIONS / TPR;
+        const int row_l = tid / TPR, s4 = tid % TPR;
         const long long row = (long long)tile * kTileM + row_l;
         const bool live = row < p.M;
         const int A = p.A;
-        float lg[OC_POLICY_MAX_ACTIONS];
+        float l[NA];
 #pragma unroll
-        for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
-            lg[a] = hpA[(row_l * 2) * 8 + a] + hpA[(row_l * 2 + 1) * 8 + a] + sS->b3[a];
-        if (live && s4 == 0) {
-            if (p.logits) {
+        for (int h = 0; h < NA; ++h) {
+            const int a = s4 + TPR * h;
+            float v = sS->b3[a];
 #pragma unroll
-                for (int a = 0; a < OC_POLICY_MAX_ACTIONS; ++a)
-                    if (a < A) p.logits[row * A + a] = lg[a];
-            }
-            if (p.value) p.value[row] = hpC[row_l * 2] + hpC[row_l * 2 + 1] + sS->b3c;
+            for (int g = 0; g < NG; ++g) v += hpA[(row_l * NG + g) * 8 + a];      // fixed order: deterministic
+            l[h] = v;
+            if (live && a < A && p.logits) p.logits[row * A + a] = v;
+        }
+        if (live && s4 == TPR - 1 && p.value) {
+            float v = sS->b3c;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) v += hpC[row_l * NG + g];
+            p.value[row] = v;
         }
         if (p.key) {
             int arg;
             float lp;
-            sample_row4(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(p.M * A), live ? row : 0, A, s4, lg, arg, lp);
+            sample_lanes<TPR>(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(p.M * A), live ? row : 0, A, s4, l, arg, lp);
             if (live && s4 == 0) {
                 if (p.action) p.action[row] = arg;
                 if (p.log_prob) p.log_prob[row] = lp;
             }
         }
-    }
     };
 
     // Software pipeline over this CTA's tiles: while the tensor cores run layer 2 of tile t into one half of TMEM, the
     // warps do the heads of tile t-1 from the other half and then layer 1 of tile t+1.
     uint32_t phase0 = 0, phase1 = 0;
+    bool w2_ready = false;
     long long prev = -1;
     int buf = 0;
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
@@ -595,7 +617,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
         }
         // ------------------------------------------------------------------ layer 1: one row per warp, 8 rounds
 #pragma unroll 1
-        for (int rr = 0; rr < kTileM / kPolWarps; rr += 2) {
+        for (int rr = 0; rr < RND; rr += 2) {
             if (PL > 0) {
                 do_row(pfA, tile, rr);
                 do_row(pfB, tile, rr + 1);
@@ -609,6 +631,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) oc_policy_kernel(const PParams
 
         // ------------------------------------------------------------------ layer 2: 2 nets x 8 K-steps on the tensor cores
         if (tid == 0) {
+            if (!w2_ready) { mbar_wait(bar_u + 24, 0u); w2_ready = true; }
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
             for (int net = 0; net < 2; ++net) {
@@ -858,7 +881,7 @@ int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pick_kernel(p->act, p->pl)<<<grid, kPolThreads, p->smem_bytes, stream>>>(k);
+    pick_kernel(p->act, p->pl)<<<grid, kObsWarps * 32, p->smem_bytes, stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
 }
 
@@ -869,7 +892,7 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     if ((action || log_prob) && !key) return OC_ERR_INVALID_ARG;
     if (N == 0) return OC_OK;
     const int64_t M = 2 * N;
-    if (M * p->A > 0x7fffffffll) return OC_ERR_INVALID_ARG;
+    if (M * p->A > 0x7fffffffll || M * p->layout->cell_stride > 0x7fffffffll) return OC_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(key) |
          reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(log_prob)) & 3u)
         return OC_ERR_ALIGNMENT;
@@ -884,7 +907,7 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     k.cell_stride = p->layout->cell_stride; k.cell_agents = p->layout->cell_agents; k.n_scan = p->layout->host.n_scan;
     k.C = p->layout->host.C;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
-    pick_kernel(p->act, 0)<<<grid, kPolThreads, p->smem_bytes, static_cast<cudaStream_t>(stream_)>>>(k);
+    pick_kernel(p->act, 0)<<<grid, kCellWarps * 32, p->smem_bytes, static_cast<cudaStream_t>(stream_)>>>(k);
     return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
 }
 
