@@ -117,12 +117,19 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
     const bool with_cells = kp.cells != nullptr;
+    if (with_cells && !aligned16(kp.cells)) return OC_ERR_ALIGNMENT;
     void (*kern)(const KParams) = with_cells ? oc_env_kernel<MODE, true> : oc_env_kernel<MODE, false>;
+    // the compact observations of a tile are staged per warp, behind the warp's regular shared-memory area
+    const int cells_smem = with_cells ? lay->epw * lay->cell_stride : 0;
+    const int smem_bytes = lay->smem_bytes + lay->warps * cells_smem;
+    if (smem_bytes > 227 * 1024) return OC_ERR_UNSUPPORTED_LAYOUT;
+    kp.cells_off = lay->warp_bytes;
+    kp.warp_bytes = lay->warp_bytes + cells_smem;
     if (lay->occ[MODE + (with_cells ? 3 : 0)] == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, lay->smem_bytes) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, smem_bytes) != cudaSuccess)
             return fail_cuda();
         lay->occ[MODE + (with_cells ? 3 : 0)] = nb < 1 ? 1 : nb;
     }
@@ -139,7 +146,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);
     cfg.blockDim = dim3((unsigned)lay->warps * 32);
-    cfg.dynamicSmemBytes = (size_t)lay->smem_bytes;
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

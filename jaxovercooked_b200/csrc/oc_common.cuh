@@ -51,7 +51,7 @@ struct KParams {
     uint8_t *done;
     oc_step_extras ex;
     uint8_t *cells;       // compact observation (scan-cell codes, agent cells, urgency), or NULL
-    int cell_stride, cell_agents;
+    int cell_stride, cell_agents, cells_off;   // cells_off: staging area inside the warp's shared memory (CELLS launches)
     int epw;        // environments per warp tile: 16, 8, 4 or 2
     int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
     int warp_bytes; // shared memory per warp

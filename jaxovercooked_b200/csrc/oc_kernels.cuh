@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
     uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] urgency flags
     const uint32_t tbar = smem_u32(s_ap + 2 * epw);                                    // this warp's mbarrier (8 bytes)
+    unsigned char *s_cells = wbase + p.cells_off;        // CELLS: [epw][cell_stride] staging of the compact observations
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
     bool bulk_pending = false;
@@ -145,6 +146,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (CELLS)         // padding bytes of the compact form stay 0xFF
+        for (int i = lane; i < (epw * p.cell_stride) >> 2; i += 32) reinterpret_cast<uint32_t *>(s_cells)[i] = 0xffffffffu;
     __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
     asm volatile("griddepcontrol.wait;" ::: "memory");
     long long tile = (long long)blockIdx.x * cta_warps + warp;
@@ -398,18 +401,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     if (o == 8 ? (st != 23) : (o != 2 && o != 10))
                         stage_record(el * C + (int)(sc >> 16), (o == 8) ? kCodePot + min(st, 23) : min(o, 10));
                     if (CELLS)     // the compact form of this observation (include/oc_b200.h, oc_step_extras.cells)
-                        p.cells[(env0 + el) * p.cell_stride + (f - el * p.n_scan)] =
+                        s_cells[el * p.cell_stride + (f - el * p.n_scan)] =
                             (uint8_t)((o == 8 ? (st != 23) : (o != 2 && o != 10)) ? ((o == 8) ? kCodePot + min(st, 23) : min(o, 10)) : 0xff);
                 }
             }
             __syncwarp();
             // (4c) agent cells show the agent, its direction and what it holds (:313-323, :345-353)
             if (active) stage_record(es * C + ny * w + nx, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)));
-            if (CELLS && active) {
-                uint8_t *cl = p.cells + env * p.cell_stride + p.cell_agents;
-                const int code = kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2));
-                *reinterpret_cast<unsigned short *>(cl + 2 * ai) = (unsigned short)((ny * w + nx) | (code << 8));
-                if (ai == 0) cl[4] = urg ? 1 : 0;
+            if (CELLS) {
+                if (active) {
+                    unsigned char *cl = s_cells + es * p.cell_stride + p.cell_agents;
+                    const int code = kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2));
+                    *reinterpret_cast<unsigned short *>(cl + 2 * ai) = (unsigned short)((ny * w + nx) | (code << 8));
+                    if (ai == 0) cl[4] = urg ? 1 : 0;
+                }
+                __syncwarp();
+                // the tile's compact observations are contiguous in global memory: 16-byte stores
+                const uint4 *src = reinterpret_cast<const uint4 *>(s_cells);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.cells + env0 * p.cell_stride);
+                for (int i = lane; i < (n_valid * p.cell_stride) >> 4; i += 32) dst[i] = src[i];
             }
             __syncwarp();
             // (4d) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left
