@@ -5,7 +5,7 @@
 //   value  = Dense_5(act(Dense_4(act(Dense_3(x)))))[:, 0]    critic  K -> 128 -> 128 -> 1
 //   x      = one uint8 observation row (h*w*26 bytes, > 95 % of them equal to the layout's static image)
 //
-// One persistent CTA per SM (16 warps) walks 128-row tiles:
+// One persistent CTA per SM (16 warps; 32 for the compact source below) walks 128-row tiles:
 //   layer 1  (sparse, CUDA cores, fp32): each warp owns a row.  It XORs the row against the observation template
 //            in 16-byte pieces, turns the few differing bytes into (k, delta) entries in shared memory and
 //            accumulates base + sum(delta * W1[k, :]) with lane j holding hidden units 8j..8j+7 of the 256
@@ -14,9 +14,11 @@
 //   layer 2  (dense, tensor cores): the activated hidden tile is written as fp16 in the 128-byte-swizzled K-major
 //            layout tcgen05 reads; one thread issues 2 x 8 tcgen05.mma (M128 N128 K16, fp32 accumulators in TMEM
 //            columns 0..127 actor / 128..255 critic) against the resident fp16 W2 images, then tcgen05.commit.
-//   heads    all 16 warps read their TMEM quadrant / 64-column group with tcgen05.ld, apply bias + activation and
-//            the 128 -> A / 128 -> 1 heads on CUDA cores; 128 threads finish the row: logits, value and, when a key
-//            is given, the categorical draw (threefry gumbel, argmax) and its log-probability.
+//   heads    all warps read their TMEM quadrant / column group with tcgen05.ld, apply bias + activation and the
+//            128 -> A / 128 -> 1 heads on CUDA cores; 4-8 lanes per row finish it: logits, value and, when a key is
+//            given, the categorical draw (threefry gumbel, argmax) and its log-probability.
+//   Rows produced by the env kernel need not be scanned at all: oc_policy_forward_cells reads the env kernel's compact
+//   observations (oc_step_extras.cells) and layer 1 becomes base + a few rows of a precomputed (cell, code) table.
 //
 // Layer 1 is 1.5 kFMA per row when done sparsely against 133 kMAC densely; layer 2 has no sparsity, which is where
 // the tensor cores pay (DESIGN.md section 9 has the numbers).
@@ -60,12 +62,12 @@ constexpr int kOffA = 0;
 constexpr int kOffW2 = kOffA + 2 * kNetBytes;
 constexpr int kOffSmall = kOffW2 + 2 * kNetBytes;
 constexpr int kOffHpA = kOffSmall + (int)sizeof(PolicySmall);
-constexpr int kOffHpC = kOffHpA + kTileM * 8 * 8 * 4;      // head partials: up to 8 column slices
+constexpr int kOffHpC = kOffHpA + kTileM * 8 * 8 * 4;      // head partials [128 rows][<= 4 column groups][8], room for two sets
 constexpr int kOffList = kOffHpC + kTileM * 8 * 4;
-constexpr int kOffMask = kOffList + kObsWarps * kListWords * 4;
-constexpr int kOffBar = kOffMask + 16 * 2 * 16;
+constexpr int kOffScan = kOffList + kObsWarps * kListWords * 4;   // scan slot -> cell table of the compact source (<= 64 B)
+constexpr int kOffBar = kOffScan + 16 * 2 * 16;
 constexpr int kOffTmpl = kOffBar + 48;      // two accumulator barriers, the TMEM base address, the W2 barrier
-static_assert(kOffHpA % 16 == 0 && kOffList % 16 == 0 && kOffMask % 16 == 0 && kOffTmpl % 16 == 0, "alignment");
+static_assert(kOffHpA % 16 == 0 && kOffList % 16 == 0 && kOffScan % 16 == 0 && kOffTmpl % 16 == 0, "alignment");
 
 struct PParams {
     const __half *w1;           // [K][256] fp16
@@ -295,8 +297,8 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     uint8_t *sA = sm + kOffA;
     uint8_t *sW2 = sm + kOffW2;
     PolicySmall *sS = reinterpret_cast<PolicySmall *>(sm + kOffSmall);
-    float *hpA = reinterpret_cast<float *>(sm + kOffHpA);      // [128][2][8]
-    float *hpC = reinterpret_cast<float *>(sm + kOffHpC);      // [128][2]
+    float *hpA = reinterpret_cast<float *>(sm + kOffHpA);      // actor head partials  [128 rows][NG column groups][8]
+    float *hpC = reinterpret_cast<float *>(sm + kOffHpC);      // critic head partials [128 rows][NG]
     uint32_t *lists = reinterpret_cast<uint32_t *>(sm + kOffList);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + kOffBar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 16);
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
                 tmplv[i] = __ldg(p.tmpl + (j - a + K) % K);
             }
         } else {
-            for (int i = tid; i < p.n_scan; i += kPolThreads) sm[kOffMask + i] = __ldg(p.scan_cells + i);
+            for (int i = tid; i < p.n_scan; i += kPolThreads) sm[kOffScan + i] = __ldg(p.scan_cells + i);
         }
     }
     if (warp == 0) {
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t sA_u = smem_addr(sA), sW2_u = smem_addr(sW2), bar_u = smem_addr(mbar);
-    uint32_t *list = lists + warp * kListWords;
+    uint32_t *list = lists + (warp & (kObsWarps - 1)) * kListWords;     // (k, delta) entries of this warp (uint8 source only)
 
     // Each warp walks the rows rr*16 + warp (rr = 0..7) of its CTA's tiles; the observation pieces of the next two
     // rows are always in flight in registers (pfA / pfB), also across the tile boundary and the layer-2 phase.
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
         load_cells(p, blockIdx.x, warp, lane, cbA);
         load_cells(p, blockIdx.x, NW + warp, lane, cbB);
     }
-    uint8_t *s_sc = reinterpret_cast<uint8_t *>(sm + kOffMask);          // [n_scan] scan slot -> cell (cells source only)
+    uint8_t *s_sc = reinterpret_cast<uint8_t *>(sm + kOffScan);          // [n_scan] scan slot -> cell (cells source only)
 
     auto finish_row = [&](const int row_l, float (&acc)[8]) {
         // activation, fp16, swizzled K-major store: lane -> net = lane >> 4, 16-byte chunk j = lane & 15 of the row
