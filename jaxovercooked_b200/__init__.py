@@ -14,7 +14,7 @@ __version__ = "0.1.0"
 
 _LAZY = {"Overcooked": "env", "State": "env", "make": "env", "vmap": "env", "registered_envs": "env",
          "Actions": "env", "LogWrapper": "wrappers", "LogEnvState": "wrappers", "CTRolloutManager": "wrappers", "random": None, "env": None,
-         "wrappers": None, "dist": None, "rollout": None, "RolloutBuffer": "rollout", "policy": None,
+         "wrappers": None, "dist": None, "rollout": None, "RolloutBuffer": "rollout", "PolicyRollout": "rollout", "policy": None,
          "ActorCritic": "policy"}
 
 

@@ -55,11 +55,13 @@ class LazySplit:
         return split(self.key, self.num, first=self.first, count=self.count, impl=impl)
 
 
-def split_chain(key, n, *, impl="threefry_legacy"):
-    """n times `key, sub = split(key)`: returns the n subkeys u32[n,2] and advances `key` IN PLACE."""
+def split_chain(key, n, *, impl="threefry_legacy", out=None):
+    """n times `key, sub = split(key)`: returns the n subkeys u32[n,2] (in `out` if given) and advances `key` IN PLACE."""
     if key.dtype != torch.uint32 or tuple(key.shape) != (2,) or not key.is_cuda or not key.is_contiguous():
         raise ValueError("key must be a contiguous uint32 CUDA tensor of shape [2]")
-    subs = torch.empty((n, 2), dtype=torch.uint32, device=key.device)
+    subs = torch.empty((n, 2), dtype=torch.uint32, device=key.device) if out is None else out
+    if subs.dtype != torch.uint32 or tuple(subs.shape) != (n, 2) or not subs.is_contiguous() or subs.device != key.device:
+        raise ValueError("out must be a contiguous uint32 tensor of shape [n, 2] on the key's device")
     lib = _lib.load()
     with torch.cuda.device(key.device):
         _lib.check(lib.oc_prng_chain(_MODES[impl], key.data_ptr(), n, subs.data_ptr(),

@@ -257,3 +257,54 @@ def test_forward_cells_needs_a_layout():
     P = net.params_from_numpy(po.make_params(1, 520))
     with pytest.raises(ocb._lib.OcError):
         net.act_cells(P, torch.zeros((4, 16), dtype=torch.uint8, device="cuda"), jr.PRNGKey(0))
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_policy_rollout_equals_the_stepwise_loop(graph):
+    """PolicyRollout (one CUDA graph per rollout) against the reference-shaped loop written out step by step with the same
+    keys: actions, observations, rewards and dones identical; two consecutive rollouts continue the same trajectory."""
+    n, T = 96, 12
+    lay = ocb.overcooked_layouts["cramped_room"]
+    params = po.make_params(11, 520)
+    params["params"]["Dense_2"]["kernel"] = (params["params"]["Dense_2"]["kernel"] * np.float32(300)).astype(np.float32)
+
+    def fresh():
+        env = ocb.make("overcooked", layout=lay, max_steps=17)
+        net = ActorCritic(6)
+        P = net.params_from_numpy(params)
+        rng = jr.PRNGKey(21)
+        rng, sub = jr.split(rng)
+        _, state = env.reset(jr.split(sub, n))
+        return env, net, P, state, rng.clone()
+
+    env, net, P, state, rng = fresh()
+    ro = ocb.PolicyRollout(env, net, P, state, rng, T, graph=graph)
+    got = []
+    for _ in range(2):
+        ro.run()
+        got.append({k: getattr(ro, k).clone() for k in ("obs", "action", "log_prob", "value", "reward", "shaped", "done")})
+    assert ro.transition_obs().shape == (T, 2 * n, 520) and ro.last_obs().shape == (2 * n, 520)
+    assert ro.transition_reward(0.5).shape == (T, 2 * n) and ro.transition_done().shape == (T, 2 * n)
+    torch.testing.assert_close(ro.transition_reward(0.5)[:, n:], ro.reward + 0.5 * ro.shaped[:, 1], rtol=0, atol=0)
+
+    env, net, P, state, rng = fresh()
+    net.bind(P, env=env)
+    cells = env.empty_cells(n)
+    obs = env.get_obs(state, cells=cells)
+    for r in range(2):
+        subs = jr.split_chain(rng, 2 * T)
+        assert torch.equal(got[r]["obs"][0, 0], obs["agent_0"]) and torch.equal(got[r]["obs"][0, 1], obs["agent_1"])
+        for t in range(T):
+            action, log_prob, value = net.act_cells(P, cells, subs[2 * t])
+            assert torch.equal(action, got[r]["action"][t]), f"rollout {r} step {t}: actions differ"
+            torch.testing.assert_close(log_prob, got[r]["log_prob"][t], rtol=0, atol=0)
+            torch.testing.assert_close(value, got[r]["value"][t], rtol=0, atol=0)
+            out = {"obs0": torch.empty_like(obs["agent_0"]), "obs1": torch.empty_like(obs["agent_1"]),
+                   "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
+                   "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"), "cells": cells}
+            obs, state, reward, done, info = env.step(jr.split(subs[2 * t + 1], n), state,
+                                                      {"agent_0": action[:n], "agent_1": action[n:]}, out=out)
+            assert torch.equal(obs["agent_0"], got[r]["obs"][t + 1, 0]) and torch.equal(obs["agent_1"], got[r]["obs"][t + 1, 1])
+            assert torch.equal(reward["agent_0"], got[r]["reward"][t]) and torch.equal(done["__all__"], got[r]["done"][t])
+            assert torch.equal(info["shaped_reward"]["agent_1"], got[r]["shaped"][t, 1])
+    assert bool(got[0]["done"].any() or got[1]["done"].any()), "no episode ended: the auto-reset was not exercised"
