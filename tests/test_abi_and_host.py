@@ -92,3 +92,26 @@ def test_all_registered_layouts_satisfy_the_abi_contract():
         for k in ("goal_idx", "pot_idx", "onion_pile_idx", "plate_pile_idx"):
             assert all(int(i) in walls for i in l[k]), (name, k)
         assert len(l["agent_idx"]) == 2 and all(int(i) not in walls for i in l["agent_idx"])
+
+
+def test_actor_critic_host_mirror_without_a_gpu():
+    """Parameter pytree, initialiser scales and argument checks of the policy mirror (architectures/mlp.py:26-53); the
+    forward itself needs the GPU and must refuse anything else instead of falling back."""
+    import numpy as np
+    import torch
+    from jaxovercooked_b200.policy import ActorCritic, LAYERS
+
+    net = ActorCritic(6, activation="something-else")          # mlp.py:20-23: anything but "relu" means tanh
+    assert net.activation == "tanh"
+    params = net.init(3, 520, device="cpu")
+    assert tuple(params["params"]) == LAYERS
+    shapes = {n: tuple(params["params"][n]["kernel"].shape) for n in LAYERS}
+    assert shapes == {"Dense_0": (520, 128), "Dense_1": (128, 128), "Dense_2": (128, 6),
+                      "Dense_3": (520, 128), "Dense_4": (128, 128), "Dense_5": (128, 1)}
+    for name, scale in (("Dense_0", 2 ** 0.5), ("Dense_1", 2 ** 0.5), ("Dense_2", 0.01), ("Dense_5", 1.0)):
+        k = params["params"][name]["kernel"].double()
+        gram = k.T @ k if k.shape[0] >= k.shape[1] else k @ k.T
+        np.testing.assert_allclose(gram.numpy(), scale * scale * np.eye(gram.shape[0]), atol=1e-5)
+        assert float(params["params"][name]["bias"].abs().max()) == 0.0
+    with pytest.raises(ValueError):                              # CPU tensors are not silently computed on the host
+        net.apply(params, torch.zeros((4, 520), dtype=torch.uint8))
