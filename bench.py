@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
+    ap.add_argument("--emit-cells", action="store_true",
+                    help="also write the compact observations (oc_step_extras.cells) every step, without a policy consuming them")
     ap.add_argument("--policy-input", default="cells", choices=["cells", "obs"],
                     help="with --policy: read the env kernel's compact observations (default) or scan the uint8 observations")
     ap.add_argument("--policy", action="store_true",
@@ -269,6 +271,9 @@ def run_ours(args):
              "shaped1": torch.empty(N, dtype=torch.float32, device=dev),
              "done": torch.empty(N, dtype=torch.bool, device=dev)} for i in range(OBS_SLOTS)]
     net = params = pol_out = None
+    if args.emit_cells and not args.policy:
+        for i in range(OBS_SLOTS):
+            outs[i]["cells"] = env.empty_cells(N)
     if args.policy:
         from jaxovercooked_b200.policy import ActorCritic
         assert R == OBS_SLOTS, "--policy reads each env batch's previous observations: needs --rotate == OBS_SLOTS"
@@ -454,7 +459,7 @@ def run_ours(args):
                                  if graph is not None else "eager launches",
                        "keys": "per-step subkeys from the split chain; per-env split fused in the kernel",
                        "actions": "i.i.d. uniform {0..5}, re-drawn on the device every 8 steps inside the timed region",
-                       "log_wrapper": bool(args.log_wrapper), "parallelism": f"env-sharded x{world}, no per-step comms"},
+                       "log_wrapper": bool(args.log_wrapper), "emit_cells": bool(args.emit_cells or args.policy), "parallelism": f"env-sharded x{world}, no per-step comms"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
     if args.policy:
         line["metric"] = METRIC + ", rollout step = actor-critic forward + sample + env step"

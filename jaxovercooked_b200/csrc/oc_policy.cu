@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -80,6 +81,7 @@ struct PParams {
     int K, A, part;
     int nvar, gshift, tv_stride;
     int n_tiles;
+    int rpt;                    // rows per tile: 128, or 64 / 32 when that is what it takes to give every SM a tile
     float *logits, *value, *log_prob;
     const uint32_t *key;
     int32_t *action;
@@ -235,14 +237,14 @@ __device__ __forceinline__ void gather_rows(const __half *__restrict__ w1, uint3
 }
 
 // this lane's 16-byte pieces of one observation row (piece 32*g + lane), issued together so that one DRAM round trip
-// covers the row; rows past the end load nothing.  Row `row_l` of tile `tile` starts at byte a0 + (tile*128 + row_l)*K of
-// the 16-byte aligned stream; tile*128*K is a multiple of 16, so everything but the tile offset is 32-bit arithmetic.
+// covers the row; rows past the end load nothing.  Row `row_l` of tile `tile` starts at byte a0 + (tile*rpt + row_l)*K of
+// the 16-byte aligned stream; tile*rpt*K is a multiple of 16 (rpt >= 32), so everything but the tile offset is 32-bit arithmetic.
 template <int PL>
 __device__ __forceinline__ void load_row(const PParams &p, long long tile, int row_l, int lane, uint4 (&pf)[PL]) {
-    if (tile < p.n_tiles && tile * kTileM + row_l < p.M) {
+    if (tile < p.n_tiles && row_l < p.rpt && tile * p.rpt + row_l < p.M) {
         const int local = p.a0 + row_l * p.K;
         const int np = ((local & 15) + p.K + 15) >> 4;
-        const uint4 *src = p.obs16 + tile * (long long)(kTileM / 16 * p.K) + (local >> 4);
+        const uint4 *src = p.obs16 + tile * (long long)(p.rpt / 16 * p.K) + (local >> 4);
 #pragma unroll
         for (int g = 0; g < PL; ++g) {
             const int q = g * 32 + lane;
@@ -272,8 +274,8 @@ __device__ __forceinline__ int emit_piece(uint32_t *list, int pos, const uint4 &
 
 // this lane's bytes of one env's compact observation (slots lane and lane + 32); 32-bit arithmetic: 2N * cell_stride < 2^31
 __device__ __forceinline__ void load_cells(const PParams &p, long long tile, int row_l, int lane, uint32_t (&cb)[2]) {
-    if (tile < p.n_tiles) {
-        const int row = (int)tile * kTileM + row_l, n = (int)p.N;
+    if (tile < p.n_tiles && row_l < p.rpt) {
+        const int row = (int)tile * p.rpt + row_l, n = (int)p.N;
         if (row < 2 * n) {
             const uint8_t *src = p.cells + (unsigned)((row >= n ? row - n : row) * p.cell_stride + lane);
             cb[0] = lane < p.cell_stride ? __ldg(src) : 0xffu;
@@ -307,6 +309,9 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.K;
 
+    // Programmatic dependent launch: the next kernel in the stream (the env step) may start its prologue now, and this
+    // kernel's own set-up -- parameters only -- runs while the previous kernel (the env step that writes the rows) drains.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     // ---- one-time setup: resident W2 images, small parameters, template variants, TMEM, mbarrier
     {
         const uint4 *s2 = reinterpret_cast<const uint4 *>(p.small);
@@ -346,6 +351,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t sA_u = smem_addr(sA), sW2_u = smem_addr(sW2), bar_u = smem_addr(mbar);
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");           // the rows (and the key) are complete from here on
     uint32_t *list = lists + (warp & (kObsWarps - 1)) * kListWords;     // (k, delta) entries of this warp (uint8 source only)
 
     // Each warp walks the rows rr*16 + warp (rr = 0..7) of its CTA's tiles; the observation pieces of the next two
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     int *wl = reinterpret_cast<int *>(lists) + warp * 72;        // this warp's compacted table rows (<= 62 + padding)
     auto do_row_cells = [&](uint32_t (&cb)[2], const long long tile, const int rr) {
         const int row_l = rr * NW + warp;
-        const int row = (int)tile * kTileM + row_l;
+        const int row = row_l < p.rpt ? (int)tile * p.rpt + row_l : (int)p.M;
         float acc[8];
         {
             const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
             acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
         }
         int n = 0;
-        if (tile * kTileM + row_l < p.M) {
+        if (row_l < p.rpt && tile * p.rpt + row_l < p.M) {
             const int local = p.a0 + row_l * K;
             const int a = local & 15;
             const int np = (a + K + 15) >> 4;
@@ -535,6 +541,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     auto do_heads = [&](const int buf) {
         constexpr int GC = kHid / NG;                        // columns per group
         const int qd = warp & 3, grp = warp >> 2, net = grp / NG, part = grp % NG;
+        if (32 * qd >= p.rpt) return;                         // short tiles: these TMEM lanes hold no rows
         const int row_l = 32 * qd + lane;
         const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(buf * kHid2 + net * kHid + part * GC);
         if (net == 0) {
@@ -577,8 +584,8 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     auto do_finish = [&](const long long tile) {
         constexpr int NA = OC_POLICY_MAX_ACTIONS / TPR;
         const int row_l = tid / TPR, s4 = tid % TPR;
-        const long long row = (long long)tile * kTileM + row_l;
-        const bool live = row < p.M;
+        const long long row = (long long)tile * p.rpt + row_l;
+        const bool live = row_l < p.rpt && row < p.M;
         const int A = p.A;
         float l[NA];
 #pragma unroll
@@ -745,6 +752,18 @@ pol_kernel_t pick_kernel(int act, int pl) {
     return pl == 2 ? oc_policy_kernel<OC_ACT_TANH, 2> : pl == 4 ? oc_policy_kernel<OC_ACT_TANH, 4> : oc_policy_kernel<OC_ACT_TANH, 8>;
 }
 
+// small batches: shorter tiles (the MMA stays M = 128, the unused rows are never read back) as long as the tiles still
+// fit in one wave of CTAs
+int rows_per_tile(long long M, int num_sms) {
+    int rpt = kTileM;
+    while (rpt > 32 && (M + rpt / 2 - 1) / (rpt / 2) <= num_sms) rpt >>= 1;
+    return rpt;
+}
+
+// Launch with programmatic stream serialization unless the parameters were repacked since the last forward (then the
+// set-up must not overtake the pack kernel).
+int launch_policy(const oc_policy *p, pol_kernel_t kern, int grid, int threads, const PParams &k, cudaStream_t stream);
+
 int gcd16(int k) {
     int g = 16;
     while (k % g) g >>= 1;
@@ -767,7 +786,27 @@ struct oc_policy {
     const oc_layout *layout;
     __half *emb;
     uint8_t *scan_cells;
+    mutable bool repacked;      // set by create / update, cleared by the next forward
 };
+
+namespace {
+int launch_policy(const oc_policy *p, pol_kernel_t kern, int grid, int threads, const PParams &k, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = p->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool use_pdl = [] { const char *e = std::getenv("OC_B200_POLICY_PDL"); return !(e && e[0] == '0'); }();
+    cfg.numAttrs = (p->repacked || !use_pdl) ? 0 : 1;
+    p->repacked = false;
+    return cudaLaunchKernelEx(&cfg, kern, k) == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+}
+}  // namespace
 
 extern "C" {
 
@@ -779,6 +818,7 @@ static int policy_pack(oc_policy *p, const oc_policy_desc *d, cudaStream_t strea
         a.bias[i] = d->bias[i];
     }
     a.tmpl = p->tmpl; a.w1 = p->w1; a.w2img = p->w2img; a.small = p->small; a.K = p->K; a.A = p->A;
+    p->repacked = true;
     oc_policy_pack_kernel<<<p->num_sms * 2, 256, 0, stream>>>(a);
     if (p->layout)
         oc_policy_embed_kernel<<<p->layout->host.C * OC_NUM_CELL_CODES + 2, kHid2, 0, stream>>>(
@@ -879,12 +919,12 @@ int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *
     k.obs16 = reinterpret_cast<const uint4 *>(ob - (uintptr_t)k.a0);
     k.M = M; k.K = p->K; k.A = p->A; k.part = p->part;
     k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
-    k.n_tiles = (int)((M + kTileM - 1) / kTileM);
+    k.rpt = rows_per_tile(M, p->num_sms);
+    k.n_tiles = (int)((M + k.rpt - 1) / k.rpt);
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pick_kernel(p->act, p->pl)<<<grid, kObsWarps * 32, p->smem_bytes, stream>>>(k);
-    return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+    return launch_policy(p, pick_kernel(p->act, p->pl), grid, kObsWarps * 32, k, stream);
 }
 
 int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells, float *logits, float *value,
@@ -903,14 +943,14 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     k.w1 = p->w1; k.w2img = p->w2img; k.small = p->small; k.tmpl = p->tmpl;
     k.M = M; k.N = N; k.K = p->K; k.A = p->A; k.part = p->part;
     k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
-    k.n_tiles = (int)((M + kTileM - 1) / kTileM);
+    k.rpt = rows_per_tile(M, p->num_sms);
+    k.n_tiles = (int)((M + k.rpt - 1) / k.rpt);
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     k.cells = cells; k.emb = p->emb; k.scan_cells = p->scan_cells;
     k.cell_stride = p->layout->cell_stride; k.cell_agents = p->layout->cell_agents; k.n_scan = p->layout->host.n_scan;
     k.C = p->layout->host.C;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
-    pick_kernel(p->act, 0)<<<grid, kCellWarps * 32, p->smem_bytes, static_cast<cudaStream_t>(stream_)>>>(k);
-    return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
+    return launch_policy(p, pick_kernel(p->act, 0), grid, kCellWarps * 32, k, static_cast<cudaStream_t>(stream_));
 }
 
 int oc_policy_sample(int prng_mode, int64_t M, int32_t A, const float *logits, const uint32_t *key, int32_t *action,
