@@ -215,13 +215,14 @@ def test_cells_are_the_observations(layout, padded, random_reset):
     assert int((cells[:, : env.info.n_scan] != 255).sum()) > 0, "no scan cell ever deviated: the test did not exercise them"
 
 
-@pytest.mark.parametrize("layout,padded", [("cramped_room", False), ("coord_ring", True), ("bottleneck_large", False)])
-def test_forward_cells_matches_forward_on_observations(layout, padded):
+@pytest.mark.parametrize("layout,padded,act", [("cramped_room", False, "tanh"), ("coord_ring", True, "tanh"),
+                                               ("bottleneck_large", False, "tanh"), ("cramped_room", False, "relu")])
+def test_forward_cells_matches_forward_on_observations(layout, padded, act):
     lay = ocb.cl_sequence_padded()[layout] if padded else ocb.overcooked_layouts[layout]
     env = ocb.make("overcooked", layout=lay, max_steps=60)
     K = env.height * env.width * 26
     n = 517
-    net = ActorCritic(6)
+    net = ActorCritic(6, activation=act)
     params = po.make_params(77, K)
     params["params"]["Dense_2"]["kernel"] = (params["params"]["Dense_2"]["kernel"] * np.float32(300)).astype(np.float32)
     P = net.params_from_numpy(params)
@@ -236,7 +237,7 @@ def test_forward_cells_matches_forward_on_observations(layout, padded):
         rng, k_act, k_step = jr.split(rng, 3)
         action, log_prob, value, logits = net.act_cells(P, cells, k_act, want_logits=True)
         batch = torch.cat([obs["agent_0"].reshape(n, -1), obs["agent_1"].reshape(n, -1)], dim=0)
-        lo, vo = po.forward(params, batch.cpu().numpy())
+        lo, vo = po.forward(params, batch.cpu().numpy(), act)
         check_outputs(logits.cpu().numpy(), value.cpu().numpy(), lo, vo, f"{layout} step {t} (cells)")
         # the observation-scanning path sees the same rows
         a2, lp2, v2, l2 = net.act(P, batch, k_act, want_logits=True)
