@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2, 4],
+                    help="step the independent env batches on this many concurrent branches of the graph (default 1: every "
+                         "launch waits for the previous one, as the steps of a single rollout do)")
     ap.add_argument("--emit-cells", action="store_true",
                     help="also write the compact observations (oc_step_extras.cells) every step, without a policy consuming them")
     ap.add_argument("--policy-input", default="cells", choices=["cells", "obs"],
@@ -337,6 +340,8 @@ def run_ours(args):
 
     side = torch.cuda.Stream(dev)
 
+    extra = [torch.cuda.Stream(dev) for _ in range(args.streams - 1)]
+
     def block(n_blocks):
         """One block = 2 x GRAPH_STEPS steps; each half's inputs are generated while the other half steps."""
         main = torch.cuda.current_stream(dev)
@@ -345,8 +350,17 @@ def run_ours(args):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     generate(1 - hf)
+                for st_ in extra:
+                    st_.wait_stream(main)
                 for i in range(GRAPH_STEPS):
-                    one_step(hf, i)
+                    lane_ = i % args.streams        # --streams > 1: independent env batches advance concurrently
+                    if lane_ == 0:
+                        one_step(hf, i)
+                    else:
+                        with torch.cuda.stream(extra[lane_ - 1]):
+                            one_step(hf, i)
+                for st_ in extra:
+                    main.wait_stream(st_)
                 main.wait_stream(side)
 
     BLOCK = 2 * GRAPH_STEPS
@@ -459,7 +473,7 @@ def run_ours(args):
                                  if graph is not None else "eager launches",
                        "keys": "per-step subkeys from the split chain; per-env split fused in the kernel",
                        "actions": "i.i.d. uniform {0..5}, re-drawn on the device every 8 steps inside the timed region",
-                       "log_wrapper": bool(args.log_wrapper), "emit_cells": bool(args.emit_cells or args.policy), "parallelism": f"env-sharded x{world}, no per-step comms"},
+                       "concurrent_branches": args.streams, "log_wrapper": bool(args.log_wrapper), "emit_cells": bool(args.emit_cells or args.policy), "parallelism": f"env-sharded x{world}, no per-step comms"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
     if args.policy:
         line["metric"] = METRIC + ", rollout step = actor-critic forward + sample + env step"
