@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define OC_B200_VERSION 100          /* 0.1.0 */
+#define OC_B200_VERSION 110          /* 0.1.1: + compact observations, oc_policy_* */
 #define OC_MAX_DIM 16                /* height, width <= 16 (reference registry max: 10 x 11) */
 #define OC_MAX_CELLS 256
 #define OC_MAX_SPECIAL 16            /* pots, goals, onion piles, plate piles: at most 16 each */

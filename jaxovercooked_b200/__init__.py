@@ -10,7 +10,7 @@ missing -- there is no CPU fallback.
 from .layouts import (Layout, overcooked_layouts, layout_grid_to_dict, pad_layouts, cl_sequence_padded,  # noqa: F401
                       hard_layouts, medium_layouts, easy_layouts, padded_layouts)
 
-__version__ = "0.1.0"
+__version__ = "0.1.1"
 
 _LAZY = {"Overcooked": "env", "State": "env", "make": "env", "vmap": "env", "registered_envs": "env",
          "Actions": "env", "LogWrapper": "wrappers", "LogEnvState": "wrappers", "CTRolloutManager": "wrappers", "random": None, "env": None,
