@@ -100,6 +100,20 @@ ffi::Error GetObsImpl(cudaStream_t stream, int64_t layout, OC_STATE_ARGS, ffi::R
     return to_error(rc, "oc_get_obs");
 }
 
+// pi, value = network.apply(params, obs_batch); action = pi.sample(seed=key); log_prob = pi.log_prob(action)
+// (baselines/IPPO_MLP.py:435-439) from the compact observations an OcStep call produced; `policy` is an oc_policy* created
+// with oc_policy_create (layout given) and refreshed with oc_policy_update after each optimiser step.
+ffi::Error PolicyActCellsImpl(cudaStream_t stream, int64_t policy, ffi::Buffer<ffi::U8> cells, ffi::Buffer<ffi::U32> key,
+                              ffi::ResultBuffer<ffi::F32> logits, ffi::ResultBuffer<ffi::F32> value,
+                              ffi::ResultBuffer<ffi::S32> action, ffi::ResultBuffer<ffi::F32> log_prob) {
+    const auto dims = cells.dimensions();                       // [N, cell_stride]
+    const int64_t n = dims.size() ? dims[0] : 0;
+    const int rc = oc_policy_forward_cells(reinterpret_cast<const oc_policy *>(policy), n, cells.typed_data(),
+                                           logits->typed_data(), value->typed_data(), key.typed_data(),
+                                           action->typed_data(), log_prob->typed_data(), stream);
+    return to_error(rc, "oc_policy_forward_cells");
+}
+
 #define OC_BIND_STATE_ARGS()                                                                                      \
     .Arg<ffi::Buffer<ffi::U32>>().Arg<ffi::Buffer<ffi::S8>>().Arg<ffi::Buffer<ffi::S32>>()                        \
         .Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::U32>>().Arg<ffi::Buffer<ffi::U32>>()                   \
@@ -146,3 +160,14 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(OcGetObs, GetObsImpl,
                                   OC_BIND_STATE_ARGS()
                                   .Ret<ffi::Buffer<ffi::U8>>()
                                   .Ret<ffi::Buffer<ffi::U8>>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcPolicyActCells, PolicyActCellsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("policy")
+                                  .Arg<ffi::Buffer<ffi::U8>>()    // cells [N, cell_stride]
+                                  .Arg<ffi::Buffer<ffi::U32>>()   // key [2]
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // logits [2N, A]
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // value [2N]
+                                  .Ret<ffi::Buffer<ffi::S32>>()   // action [2N]
+                                  .Ret<ffi::Buffer<ffi::F32>>()); // log_prob [2N]

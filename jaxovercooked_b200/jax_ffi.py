@@ -33,7 +33,8 @@ def _register():
         raise _lib.OcError(f"{_FFI_LIB} is missing: build it with __graft_entry__.build() on a machine that has JAX")
     C.CDLL(_lib.LIB_PATH, mode=C.RTLD_GLOBAL)              # the shim links against liboc_b200.so
     shim = C.CDLL(_FFI_LIB)
-    for name, sym in (("oc_step", "OcStep"), ("oc_reset", "OcReset"), ("oc_get_obs", "OcGetObs")):
+    for name, sym in (("oc_step", "OcStep"), ("oc_reset", "OcReset"), ("oc_get_obs", "OcGetObs"),
+                      ("oc_policy_act_cells", "OcPolicyActCells")):
         jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(getattr(shim, sym)), platform="CUDA")
     _registered = True
 
@@ -115,3 +116,17 @@ def bind(env, donate_state=True):
     env.step = types.MethodType(step, env)
     env.get_obs = types.MethodType(get_obs, env)
     return env
+
+
+def policy_act_cells(policy_handle, cells, key, action_dim):
+    """`action, log_prob, value, logits` for both agents of the N envs whose compact observations are `cells`
+    (uint8 [N, cell_stride], as written through `oc_step_extras.cells`): one `oc_policy_forward_cells` custom call.
+    `policy_handle` is the integer value of an `oc_policy*` (see include/oc_b200.h, oc_policy_create with a layout)."""
+    import jax
+    import jax.numpy as jnp
+    _register()
+    m = 2 * cells.shape[0]
+    outs = [jax.ShapeDtypeStruct((m, action_dim), jnp.float32), jax.ShapeDtypeStruct((m,), jnp.float32),
+            jax.ShapeDtypeStruct((m,), jnp.int32), jax.ShapeDtypeStruct((m,), jnp.float32)]
+    logits, value, action, log_prob = jax.ffi.ffi_call("oc_policy_act_cells", outs)(cells, key, policy=np.int64(policy_handle))
+    return action, log_prob, value, logits
