@@ -82,6 +82,24 @@ ffi::Error StepImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> k
     return to_error(rc, "oc_step");
 }
 
+// the same step that additionally returns the compact observations uint8[N, cell_stride] (oc_step_extras.cells), the input
+// of OcPolicyActCells
+ffi::Error StepCellsImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> keys, OC_STATE_ARGS,
+                         ffi::Buffer<ffi::S32> act0, ffi::Buffer<ffi::S32> act1, OC_STATE_RETS,
+                         ffi::ResultBuffer<ffi::U8> obs0, ffi::ResultBuffer<ffi::U8> obs1,
+                         ffi::ResultBuffer<ffi::F32> reward, ffi::ResultBuffer<ffi::F32> shaped0,
+                         ffi::ResultBuffer<ffi::F32> shaped1, ffi::ResultBuffer<ffi::PRED> done,
+                         ffi::ResultBuffer<ffi::U8> cells) {
+    const int64_t n = leading_count(keys);
+    oc_step_extras ex = {};
+    ex.cells = cells->typed_data();
+    const int rc = oc_step(reinterpret_cast<const oc_layout *>(layout), n, keys.typed_data(), OC_IN_STATE,
+                           act0.typed_data(), act1.typed_data(), /*reset_state=*/nullptr, OC_OUT_STATE,
+                           obs0->typed_data(), obs1->typed_data(), reward->typed_data(), shaped0->typed_data(),
+                           shaped1->typed_data(), reinterpret_cast<uint8_t *>(done->typed_data()), &ex, stream);
+    return to_error(rc, "oc_step");
+}
+
 // env.reset under vmap  (overcooked_environment/overcooked.py:136-248)
 ffi::Error ResetImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> keys, OC_STATE_RETS,
                      ffi::ResultBuffer<ffi::U8> obs0, ffi::ResultBuffer<ffi::U8> obs1) {
@@ -142,6 +160,24 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(OcStep, StepImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_0
                                   .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_1
                                   .Ret<ffi::Buffer<ffi::PRED>>()  // done
+);
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcStepCells, StepCellsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("layout")
+                                  .Arg<ffi::Buffer<ffi::U32>>()   // keys
+                                  OC_BIND_STATE_ARGS()
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_0 actions
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_1 actions
+                                  OC_BIND_STATE_RETS()
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // obs agent_0
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // obs agent_1
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // reward
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_0
+                                  .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_1
+                                  .Ret<ffi::Buffer<ffi::PRED>>()  // done
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // compact observations
 );
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(OcReset, ResetImpl,
