@@ -63,12 +63,15 @@ constexpr int kOffA = 0;
 constexpr int kOffW2 = kOffA + 2 * kNetBytes;
 constexpr int kOffSmall = kOffW2 + 2 * kNetBytes;
 constexpr int kOffHpA = kOffSmall + (int)sizeof(PolicySmall);
-constexpr int kOffHpC = kOffHpA + kTileM * 8 * 8 * 4;      // head partials [128 rows][<= 4 column groups][8], room for two sets
-constexpr int kOffList = kOffHpC + kTileM * 8 * 4;
-constexpr int kOffScan = kOffList + kObsWarps * kListWords * 4;   // scan slot -> cell table of the compact source (<= 64 B)
-constexpr int kOffBar = kOffScan + 16 * 2 * 16;
-constexpr int kOffTmpl = kOffBar + 48;      // two accumulator barriers, the TMEM base address, the W2 barrier
-static_assert(kOffHpA % 16 == 0 && kOffList % 16 == 0 && kOffScan % 16 == 0 && kOffTmpl % 16 == 0, "alignment");
+// everything behind the operands depends on the row source: the compact source (32 warps, 4 column groups per net) needs no
+// entry lists and no template, which leaves ~90 KB of the SM's 256 KB to L1 for the embedding-table gathers
+__host__ __device__ constexpr int off_hpc(bool cells) { return kOffHpA + kTileM * (cells ? 4 : 2) * 8 * 4; }     // actor head partials [128][NG][8]
+__host__ __device__ constexpr int off_list(bool cells) { return off_hpc(cells) + kTileM * (cells ? 4 : 2) * 4; } // critic head partials [128][NG]
+__host__ __device__ constexpr int off_scan(bool cells) { return off_list(cells) + (cells ? kCellWarps * 72 * 4 : kObsWarps * kListWords * 4); }
+__host__ __device__ constexpr int off_bar(bool cells) { return off_scan(cells) + 64; }          // scan slot -> cell table of the compact source
+__host__ __device__ constexpr int off_tmpl(bool cells) { return off_bar(cells) + 48; }          // two accumulator barriers, TMEM base address, W2 barrier
+static_assert(kOffHpA % 16 == 0 && off_list(true) % 16 == 0 && off_list(false) % 16 == 0 && off_tmpl(true) % 16 == 0 &&
+              off_tmpl(false) % 16 == 0, "alignment");
 
 struct PParams {
     const __half *w1;           // [K][256] fp16
@@ -300,11 +303,12 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     uint8_t *sW2 = sm + kOffW2;
     PolicySmall *sS = reinterpret_cast<PolicySmall *>(sm + kOffSmall);
     float *hpA = reinterpret_cast<float *>(sm + kOffHpA);      // actor head partials  [128 rows][NG column groups][8]
-    float *hpC = reinterpret_cast<float *>(sm + kOffHpC);      // critic head partials [128 rows][NG]
-    uint32_t *lists = reinterpret_cast<uint32_t *>(sm + kOffList);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + kOffBar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 16);
-    uint8_t *tmplv = sm + kOffTmpl;
+    constexpr bool kCells = PL == 0;
+    float *hpC = reinterpret_cast<float *>(sm + off_hpc(kCells));      // critic head partials [128 rows][NG]
+    uint32_t *lists = reinterpret_cast<uint32_t *>(sm + off_list(kCells));
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + off_bar(kCells));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + off_bar(kCells) + 16);
+    uint8_t *tmplv = sm + off_tmpl(kCells);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.K;
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
                 tmplv[i] = __ldg(p.tmpl + (j - a + K) % K);
             }
         } else {
-            for (int i = tid; i < p.n_scan; i += kPolThreads) sm[kOffScan + i] = __ldg(p.scan_cells + i);
+            for (int i = tid; i < p.n_scan; i += kPolThreads) sm[off_scan(kCells) + i] = __ldg(p.scan_cells + i);
         }
     }
     if (warp == 0) {
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
         load_cells(p, blockIdx.x, warp, lane, cbA);
         load_cells(p, blockIdx.x, NW + warp, lane, cbB);
     }
-    uint8_t *s_sc = reinterpret_cast<uint8_t *>(sm + kOffScan);          // [n_scan] scan slot -> cell (cells source only)
+    uint8_t *s_sc = reinterpret_cast<uint8_t *>(sm + off_scan(kCells));          // [n_scan] scan slot -> cell (cells source only)
 
     auto finish_row = [&](const int row_l, float (&acc)[8]) {
         // activation, fp16, swizzled K-major store: lane -> net = lane >> 4, 16-byte chunk j = lane & 15 of the row
@@ -762,7 +766,7 @@ int rows_per_tile(long long M, int num_sms) {
 
 // Launch with programmatic stream serialization unless the parameters were repacked since the last forward (then the
 // set-up must not overtake the pack kernel).
-int launch_policy(const oc_policy *p, pol_kernel_t kern, int grid, int threads, const PParams &k, cudaStream_t stream);
+int launch_policy(const oc_policy *p, pol_kernel_t kern, int grid, int threads, size_t smem, const PParams &k, cudaStream_t stream);
 
 int gcd16(int k) {
     int g = 16;
@@ -776,7 +780,7 @@ struct oc_policy {
     int K, A, act, part;
     int nvar, gshift, tv_stride;
     int num_sms;
-    size_t smem_bytes;
+    size_t smem_bytes, smem_cells;   // dynamic shared memory of the uint8-source / compact-source kernels
     __half *w1;
     uint8_t *w2img;
     PolicySmall *small;
@@ -790,12 +794,12 @@ struct oc_policy {
 };
 
 namespace {
-int launch_policy(const oc_policy *p, pol_kernel_t kern, int grid, int threads, const PParams &k, cudaStream_t stream) {
+int launch_policy(const oc_policy *p, pol_kernel_t kern, int grid, int threads, size_t smem, const PParams &k, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = p->smem_bytes;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -851,7 +855,8 @@ int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
     p->gshift = g == 16 ? 4 : g == 8 ? 3 : g == 4 ? 2 : g == 2 ? 1 : 0;
     p->nvar = 16 / g;
     p->tv_stride = ((p->K + 15 + 31) / 16) * 16;     // a + K bytes of template, read in whole 16-byte pieces
-    p->smem_bytes = (size_t)kOffTmpl + (size_t)p->nvar * p->tv_stride + 1024;
+    p->smem_bytes = (size_t)off_tmpl(false) + (size_t)p->nvar * p->tv_stride + 1024;
+    p->smem_cells = (size_t)off_tmpl(true) + 1024;
     const int groups = (((p->K + 30) >> 4) + 31) / 32;
     p->pl = groups <= 2 ? 2 : groups <= 4 ? 4 : 8;
     if (groups > 8 || p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return OC_ERR_UNSUPPORTED_LAYOUT; }
@@ -876,7 +881,7 @@ int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
                 return OC_ERR_CUDA;
             }
             p->layout = lay;
-            if (cudaFuncSetAttribute(pick_kernel(p->act, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
+            if (cudaFuncSetAttribute(pick_kernel(p->act, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cells) != cudaSuccess) {
                 oc_policy_destroy(p);
                 return OC_ERR_CUDA;
             }
@@ -924,7 +929,7 @@ int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    return launch_policy(p, pick_kernel(p->act, p->pl), grid, kObsWarps * 32, k, stream);
+    return launch_policy(p, pick_kernel(p->act, p->pl), grid, kObsWarps * 32, p->smem_bytes, k, stream);
 }
 
 int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells, float *logits, float *value,
@@ -950,7 +955,7 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     k.cell_stride = p->layout->cell_stride; k.cell_agents = p->layout->cell_agents; k.n_scan = p->layout->host.n_scan;
     k.C = p->layout->host.C;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
-    return launch_policy(p, pick_kernel(p->act, 0), grid, kCellWarps * 32, k, static_cast<cudaStream_t>(stream_));
+    return launch_policy(p, pick_kernel(p->act, 0), grid, kCellWarps * 32, p->smem_cells, k, static_cast<cudaStream_t>(stream_));
 }
 
 int oc_policy_sample(int prng_mode, int64_t M, int32_t A, const float *logits, const uint32_t *key, int32_t *action,
