@@ -29,3 +29,25 @@ def test_other_ranks_of_the_reference_arm_do_no_work():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["--log-wrapper"], ["--policy"], ["--streams", "2"]])
+def test_gpu_arm_prints_the_contract_line(extra):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--envs", "2048", "--steps", "64", "--warmup", "3",
+                          "--cpu-seconds", "0.5", "--e2e-steps", "64"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "u8"
+    assert "workload" in d["config"] and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    if not extra:
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 8 * 2048
+        assert d["e2e"]["value"] > 0 and d["e2e"]["value"] != d["value"]
