@@ -309,3 +309,21 @@ def test_policy_rollout_equals_the_stepwise_loop(graph):
             assert torch.equal(reward["agent_0"], got[r]["reward"][t]) and torch.equal(done["__all__"], got[r]["done"][t])
             assert torch.equal(info["shaped_reward"]["agent_1"], got[r]["shaped"][t, 1])
     assert bool(got[0]["done"].any() or got[1]["done"].any()), "no episode ended: the auto-reset was not exercised"
+
+
+def test_cells_buffer_must_be_16_byte_aligned():
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"])
+    n = 8
+    _, state = env.reset(jr.split(jr.PRNGKey(0), n))
+    base = torch.full((n * env.info.cell_stride + 8,), 255, dtype=torch.uint8, device="cuda")
+    crooked = base[8:].view(n, env.info.cell_stride)
+    with pytest.raises(ocb._lib.OcError, match="align"):
+        env.get_obs(state, cells=crooked)
+    with pytest.raises(ValueError):
+        env.step(jr.split(jr.PRNGKey(1), n), state, {"agent_0": torch.zeros(n, dtype=torch.int32, device="cuda"),
+                                                      "agent_1": torch.zeros(n, dtype=torch.int32, device="cuda")},
+                 out={"obs0": torch.empty((n, 4, 5, 26), dtype=torch.uint8, device="cuda"),
+                      "obs1": torch.empty((n, 4, 5, 26), dtype=torch.uint8, device="cuda"),
+                      "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
+                      "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"),
+                      "cells": torch.zeros((n, 3), dtype=torch.uint8, device="cuda")})
