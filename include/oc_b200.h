@@ -117,7 +117,8 @@ typedef struct {
      *   [cell_agents + 4]      1 when the urgency plane (channel 25) is set, else 0
      * Every observation is the static image with those records written over it (agent_1's view: the two agent codes
      * with bit 4 of (code - 35) flipped), plus channel 25 everywhere when urgent -- oc_policy_forward_cells consumes
-     * this instead of re-reading the 26-channel images. */
+     * this instead of re-reading the 26-channel images.  The buffer must be 16-byte aligned (OC_ERR_ALIGNMENT); padding
+     * bytes of a row are written as 0xFF. */
     uint8_t *cells;
 } oc_step_extras;
 
