@@ -327,3 +327,28 @@ def test_cells_buffer_must_be_16_byte_aligned():
                       "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
                       "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"),
                       "cells": torch.zeros((n, 3), dtype=torch.uint8, device="cuda")})
+
+
+def test_policy_rollout_with_the_fused_logwrapper():
+    """The LogWrapper trackers and the integer statistics ride along inside the rollout graph."""
+    n, T = 64, 10
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"], max_steps=7)
+    net = ActorCritic(6)
+    P = net.params_from_numpy(po.make_params(2, 520))
+    rng = jr.PRNGKey(4)
+    _, state = env.reset(jr.split(rng, n))
+    z = lambda: torch.zeros((n, 2), dtype=torch.float32, device="cuda")
+    log = {"episode_returns": z(), "episode_lengths": z(), "returned_episode_returns": z(), "returned_episode_lengths": z(),
+           "returned_episode": torch.zeros((n, 2), dtype=torch.bool, device="cuda")}
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    ro = ocb.PolicyRollout(env, net, P, state, rng, T, log=log, stats=stats)
+    done_total, reward_total = 0, 0.0
+    for _ in range(3):
+        ro.run()
+        done_total += int(ro.done.sum())
+        reward_total += float(ro.reward.sum())
+    s = stats.cpu().tolist()
+    assert s[0] == done_total == n * (3 * T // 7)            # every env finishes an episode every 7 steps
+    assert s[1] == int(reward_total) and s[6] == n * 3 * T
+    # 30 steps = 4 full episodes + 2 steps into the fifth
+    assert torch.all(log["episode_lengths"] == 2) and torch.all(log["returned_episode_lengths"] == 7)
