@@ -352,3 +352,25 @@ def test_policy_rollout_with_the_fused_logwrapper():
     assert s[1] == int(reward_total) and s[6] == n * 3 * T
     # 30 steps = 4 full episodes + 2 steps into the fifth
     assert torch.all(log["episode_lengths"] == 2) and torch.all(log["returned_episode_lengths"] == 7)
+
+
+def test_policy_rollout_is_bitwise_reproducible():
+    """Same seeds, same everything, twice: every tensor of the trajectory is bit-identical (fixed summation orders in the
+    policy kernel, integer-exact env step), also at a size that spans many tiles and several waves of CTAs."""
+    def once():
+        n, T = 20000, 6
+        env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"], max_steps=5)
+        net = ActorCritic(6)
+        params = po.make_params(13, 520)
+        params["params"]["Dense_2"]["kernel"] = (params["params"]["Dense_2"]["kernel"] * np.float32(300)).astype(np.float32)
+        P = net.params_from_numpy(params)
+        rng = jr.PRNGKey(77)
+        _, state = env.reset(jr.split(rng, n))
+        ro = ocb.PolicyRollout(env, net, P, state, rng, T)
+        ro.run()
+        ro.run()
+        return {k: getattr(ro, k).clone() for k in ("obs", "action", "log_prob", "value", "reward", "shaped", "done")}
+    a, b = once(), once()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert a["action"].float().std() > 0.5                       # the policy is not degenerate
