@@ -115,3 +115,17 @@ def test_actor_critic_host_mirror_without_a_gpu():
         assert float(params["params"][name]["bias"].abs().max()) == 0.0
     with pytest.raises(ValueError):                              # CPU tensors are not silently computed on the host
         net.apply(params, torch.zeros((4, 520), dtype=torch.uint8))
+
+
+def test_public_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C99 with no torch / CUDA / C++ types in sight."""
+    import subprocess
+    import tempfile
+    src = ('#include "oc_b200.h"\nint main(void){ oc_policy_desc d; oc_step_extras e; oc_layout_info i; oc_state s;'
+           ' (void)d; (void)e; (void)i; (void)s; return oc_version() ? 0 : 1; }\n')
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write(src)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", f.name], capture_output=True, text=True)
+    os.unlink(f.name)
+    assert r.returncode == 0, r.stderr
