@@ -374,3 +374,30 @@ def test_policy_rollout_is_bitwise_reproducible():
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert a["action"].float().std() > 0.5                       # the policy is not degenerate
+
+
+@pytest.mark.parametrize("name", sorted(ocb.overcooked_layouts))
+def test_cells_are_the_observations_on_every_layout(name):
+    """The compact form expands bit-exactly into both observations on all registered layouts (random_reset, short episodes)."""
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts[name], random_reset=True, max_steps=9)
+    if env.info.cell_stride > 64:
+        pytest.skip("more than 59 scan cells: the env still emits the compact form, the policy does not consume it")
+    n = 24
+    rng = jr.PRNGKey(len(name))
+    rng, sub = jr.split(rng)
+    _, state = env.reset(jr.split(sub, n))
+    cells = env.empty_cells(n)
+    obs = env.get_obs(state, cells=cells)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(14):
+        o0, o1 = expand_cells(env, cells.cpu().numpy())
+        np.testing.assert_array_equal(o0, obs["agent_0"].cpu().numpy(), err_msg=f"{name} step {t} agent_0")
+        np.testing.assert_array_equal(o1, obs["agent_1"].cpu().numpy(), err_msg=f"{name} step {t} agent_1")
+        rng, sub = jr.split(rng)
+        acts = {a: torch.randint(0, 6, (n,), dtype=torch.int32, device="cuda", generator=g) for a in ("agent_0", "agent_1")}
+        for a in acts:
+            acts[a][torch.rand(n, device="cuda", generator=g) < 0.35] = 5
+        out = {"obs0": torch.empty_like(obs["agent_0"]), "obs1": torch.empty_like(obs["agent_1"]),
+               "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
+               "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"), "cells": cells}
+        obs, state, *_ = env.step(jr.split(sub, n), state, acts, out=out)
