@@ -192,8 +192,9 @@ class Overcooked:
                 torch.empty(shp, dtype=torch.uint8, device=self.device))
 
     # ------------------------------------------------------------------ the reference's three calls
-    def reset(self, key):
-        """obs, state = env.reset(key)   (overcooked.py:136-248).  key: u32[..., 2]."""
+    def reset(self, key, *, cells=None):
+        """obs, state = env.reset(key)   (overcooked.py:136-248).  key: u32[..., 2].
+        `cells` (uint8 [N, cell_stride], `empty_cells`) also receives the compact form of the first observations."""
         key = self._key(key)
         batch = tuple(key.shape[:-1])
         n = int(np.prod(batch)) if batch else 1
@@ -202,6 +203,9 @@ class Overcooked:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.oc_reset(self._handle, n, key.data_ptr(), self._state_ptrs(st, batch),
                                           obs0.data_ptr(), obs1.data_ptr(), self._stream()), "oc_reset")
+            if cells is not None:
+                _lib.check(self._lib.oc_get_obs_cells(self._handle, n, self._state_ptrs(st, batch), obs0.data_ptr(),
+                                                      obs1.data_ptr(), cells.data_ptr(), self._stream()), "oc_get_obs_cells")
         return {"agent_0": obs0, "agent_1": obs1}, st
 
     def step(self, key, state, actions, reset_state=None, *, donate=False, out=None, log=None, stats=None):

@@ -385,9 +385,8 @@ def test_cells_are_the_observations_on_every_layout(name):
     n = 24
     rng = jr.PRNGKey(len(name))
     rng, sub = jr.split(rng)
-    _, state = env.reset(jr.split(sub, n))
     cells = env.empty_cells(n)
-    obs = env.get_obs(state, cells=cells)
+    obs, state = env.reset(jr.split(sub, n), cells=cells)
     g = torch.Generator(device="cuda").manual_seed(1)
     for t in range(14):
         o0, o1 = expand_cells(env, cells.cpu().numpy())
