@@ -400,3 +400,30 @@ def test_cells_are_the_observations_on_every_layout(name):
                "reward": torch.empty(n, device="cuda"), "shaped0": torch.empty(n, device="cuda"),
                "shaped1": torch.empty(n, device="cuda"), "done": torch.empty(n, dtype=torch.bool, device="cuda"), "cells": cells}
         obs, state, *_ = env.step(jr.split(sub, n), state, acts, out=out)
+
+
+@pytest.mark.parametrize("A", [1, 3, 8])
+@pytest.mark.parametrize("impl", ["threefry_legacy", "threefry_partitionable"])
+def test_other_action_counts(A, impl):
+    """1 .. OC_POLICY_MAX_ACTIONS actions: logits, value, draws and log-probabilities against the oracle."""
+    rng = np.random.default_rng(A)
+    K, M = 260, 333
+    params = po.make_params(50 + A, K, action_dim=A)
+    params["params"]["Dense_2"]["kernel"] = (params["params"]["Dense_2"]["kernel"] * np.float32(200)).astype(np.float32)
+    obs = (rng.integers(0, 5, (M, K)) * (rng.random((M, K)) < 0.04)).astype(np.uint8)
+    net = ActorCritic(A, prng_impl=impl)
+    P = net.params_from_numpy(params)
+    key_np = prng.PRNGKey(99)
+    action, log_prob, value, logits = net.act(P, torch.from_numpy(obs).cuda(), keys_to_dev(key_np), want_logits=True)
+    lo, vo = po.forward(params, obs)
+    assert logits.shape == (M, A)
+    assert np.abs(logits.cpu().numpy() - lo).max() <= TOL * max(1.0, np.abs(lo).max())
+    assert np.abs(value.cpu().numpy() - vo).max() <= TOL * max(1.0, np.abs(vo).max())
+    a_ref, z = po.sample(key_np, logits.cpu().numpy(), impl == "threefry_partitionable")
+    a = action.cpu().numpy()
+    assert a.min() >= 0 and a.max() < A
+    if A > 1:
+        top2 = np.sort(z, axis=-1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-5
+        np.testing.assert_array_equal(a[clear], a_ref[clear])
+    np.testing.assert_allclose(log_prob.cpu().numpy(), po.log_prob(logits.cpu().numpy(), a), atol=3e-6)
