@@ -275,12 +275,14 @@ __device__ __forceinline__ int emit_piece(uint32_t *list, int pos, const uint4 &
     return pos;
 }
 
-// this lane's bytes of one env's compact observation (slots lane and lane + 32); 32-bit arithmetic: 2N * cell_stride < 2^31
-__device__ __forceinline__ void load_cells(const PParams &p, long long tile, int row_l, int lane, uint32_t (&cb)[2]) {
-    if (tile < p.n_tiles && row_l < p.rpt) {
-        const int row = (int)tile * p.rpt + row_l, n = (int)p.N;
-        if (row < 2 * n) {
-            const uint8_t *src = p.cells + (unsigned)((row >= n ? row - n : row) * p.cell_stride + lane);
+// this lane's bytes of one env's compact observation (slots lane and lane + 32).  In the compact source a tile holds
+// rpt/2 environments: rows [0, rpt/2) are their agent_0 views, rows [rpt/2, rpt) the agent_1 views of the same envs.
+__device__ __forceinline__ void load_cells(const PParams &p, long long tile, int e_l, int lane, uint32_t (&cb)[2]) {
+    const int ept = p.rpt >> 1;
+    if (tile < p.n_tiles && e_l < ept) {
+        const int env = (int)tile * ept + e_l;
+        if (env < (int)p.N) {
+            const uint8_t *src = p.cells + (unsigned)(env * p.cell_stride + lane);
             cb[0] = lane < p.cell_stride ? __ldg(src) : 0xffu;
             if (p.cell_stride > 32) cb[1] = lane + 32 < p.cell_stride ? __ldg(src + 32) : 0xffu;
         }
@@ -294,7 +296,8 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     constexpr int PLA = PL > 0 ? PL : 1;
     constexpr int NW = PL > 0 ? kObsWarps : kCellWarps;     // warps per CTA
     constexpr int kPolThreads = NW * 32;
-    constexpr int RND = kTileM / NW, RSH = NW == 16 ? 3 : 2;  // rows per warp and tile (8 or 4), log2 of it
+    constexpr int RND = PL > 0 ? kTileM / NW : kTileM / 2 / NW;   // rows (uint8 source) or envs (compact source) per warp and tile
+    constexpr int RSH = RND == 8 ? 3 : RND == 4 ? 2 : 1;          // log2 of it
     constexpr int NG = NW / 8;                               // 64- or 32-column groups per net in the heads phase (2 or 4)
     constexpr int TPR = kPolThreads / kTileM;                // threads per row in the finishing phase (4 or 8)
     extern __shared__ uint8_t smem_raw[];
@@ -388,7 +391,9 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
         *reinterpret_cast<uint4 *>(dst) = pk;
     };
 
-    // layer 1 of one row from its compact observation: base + sum of the embeddings of the deviating cells.
+    // Layer 1 of BOTH agents' rows of one env from its compact observation.  The two views share everything but the agent
+    // cells: shared = base + embeddings of the deviating scan cells (+ urgency row); view v adds the two agent embeddings
+    // with the viewer bit of the codes as agent v sees them.  One decode and one set of shared gathers serve two rows.
     // What a slot means depends only on the lane, so it is decoded once: kind 1 = scan cell (table row sbase + code),
     // 2 = an agent's code (its cell is in the previous slot), 3 = urgency flag, 0 = padding.
     int kind[2], sbase[2];
@@ -398,61 +403,89 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
         kind[g] = (PL == 0 && slot < p.n_scan) ? 1 : (ag == 1 || ag == 3) ? 2 : ag == 4 ? 3 : 0;
         sbase[g] = (PL == 0 && slot < p.n_scan) ? (int)s_sc[slot] * OC_NUM_CELL_CODES : 0;
     }
-    int *wl = reinterpret_cast<int *>(lists) + warp * 72;        // this warp's compacted table rows (<= 62 + padding)
-    auto do_row_cells = [&](uint32_t (&cb)[2], const long long tile, const int rr) {
-        const int row_l = rr * NW + warp;
-        const int row = row_l < p.rpt ? (int)tile * p.rpt + row_l : (int)p.M;
-        float acc[8];
+    const int ag_slot0 = p.cell_agents + 1, ag_slot1 = p.cell_agents + 3;      // where the two agent codes sit
+    int *wl = reinterpret_cast<int *>(lists) + warp * 72;        // this warp's compacted shared table rows (<= 60 + padding)
+    auto do_env_cells = [&](uint32_t (&cb)[2], const long long tile, const int rr) {
+        const int ept = p.rpt >> 1;
+        const int e_l = rr * NW + warp;
+        const int env = e_l < ept ? (int)tile * ept + e_l : (int)p.N;
+        const bool valid_env = env < (int)p.N;
+        float acc0[8], acc1[8];
         {
             const float4 b0 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane);
             const float4 b1 = *reinterpret_cast<const float4 *>(sS->base + 8 * lane + 4);
-            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-            acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+            acc0[0] = b0.x; acc0[1] = b0.y; acc0[2] = b0.z; acc0[3] = b0.w;
+            acc0[4] = b1.x; acc0[5] = b1.y; acc0[6] = b1.z; acc0[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc1[i] = acc0[i];
         }
         int cnt = 0;
-        if (row < (int)p.M) {
-            const int flip = row >= (int)p.N ? 16 : 0;        // agent_1's rows see the agent codes with the viewer bit flipped
-            const int idx_zero = p.C * OC_NUM_CELL_CODES;
+        int a0v0 = 0, a1v0 = 0, a0v1 = 0, a1v1 = 0;             // table rows of agent 0 / 1 as seen by agent_0 / agent_1
+        const int idx_zero = p.C * OC_NUM_CELL_CODES;
+        if (valid_env) {
             const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 if (g == 1 && p.cell_stride <= 32) break;      // most layouts: one byte per lane covers the env
                 const int b = (int)cb[g];
                 const int prev = (int)__shfl_up_sync(0xffffffffu, cb[g], 1);     // an agent's cell sits one slot before its code
-                const int ix = kind[g] == 1 ? sbase[g] + b
-                             : kind[g] == 2 ? prev * OC_NUM_CELL_CODES + kCodeAgent + ((b - kCodeAgent) ^ flip)
-                                            : idx_zero + 1;
-                const bool valid = kind[g] == 1 ? b != 0xff : kind[g] == 2 ? true : kind[g] == 3 ? b != 0 : false;
+                const int ixa = prev * OC_NUM_CELL_CODES + b;                    // agent row as agent_0 sees it
+                const int ixb = prev * OC_NUM_CELL_CODES + kCodeAgent + ((b - kCodeAgent) ^ 16);   // ... as agent_1 sees it
+                if ((ag_slot0 >> 5) == g) {
+                    a0v0 = __shfl_sync(0xffffffffu, ixa, ag_slot0 & 31);
+                    a0v1 = __shfl_sync(0xffffffffu, ixb, ag_slot0 & 31);
+                }
+                if ((ag_slot1 >> 5) == g) {
+                    a1v0 = __shfl_sync(0xffffffffu, ixa, ag_slot1 & 31);
+                    a1v1 = __shfl_sync(0xffffffffu, ixb, ag_slot1 & 31);
+                }
+                const int ix = kind[g] == 1 ? sbase[g] + b : idx_zero + 1;
+                const bool valid = kind[g] == 1 ? b != 0xff : kind[g] == 3 ? b != 0 : false;
                 const unsigned bal = __ballot_sync(0xffffffffu, valid);
-                if (valid) wl[cnt + __popc(bal & lt)] = ix;      // slot order: the sum below is deterministic
+                if (valid) wl[cnt + __popc(bal & lt)] = ix;      // slot order: the sums below are deterministic
                 cnt += __popc(bal);
             }
-            if (lane < 3) wl[cnt + lane] = idx_zero;             // pad to a multiple of 4 with the zero row
+            if (lane == 0) wl[cnt] = idx_zero;                   // pad to a multiple of 2 with the zero row
             __syncwarp();
         }
-        {   // this slot is free again: fetch the row after next
+        {   // this slot is free again: fetch the env after next
             const int it2 = item + 2;
             load_cells(p, (long long)blockIdx.x + (long long)(it2 >> RSH) * gridDim.x, (it2 & (RND - 1)) * NW + warp, lane, cb);
             ++item;
         }
-        const __half *el = p.emb + 8 * lane;
-        for (int i = 0; i < cnt; i += 4) {                       // four embeddings in flight
-            const int4 ix = *reinterpret_cast<const int4 *>(wl + i);
+        if (valid_env) {
+            const __half *el = p.emb + 8 * lane;
             uint4 w[4];
-            w[0] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.x * kHid2));
-            w[1] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.y * kHid2));
-            w[2] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.z * kHid2));
-            w[3] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.w * kHid2));
+            w[0] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)a0v0 * kHid2));
+            w[1] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)a1v0 * kHid2));
+            w[2] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)a0v1 * kHid2));
+            w[3] = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)a1v1 * kHid2));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                fma_h2(acc[0], acc[1], w[u].x, (unsigned short)0x3c00);
-                fma_h2(acc[2], acc[3], w[u].y, (unsigned short)0x3c00);
-                fma_h2(acc[4], acc[5], w[u].z, (unsigned short)0x3c00);
-                fma_h2(acc[6], acc[7], w[u].w, (unsigned short)0x3c00);
+            for (int u = 0; u < 2; ++u) {
+                fma_h2(acc0[0], acc0[1], w[u].x, (unsigned short)0x3c00); fma_h2(acc0[2], acc0[3], w[u].y, (unsigned short)0x3c00);
+                fma_h2(acc0[4], acc0[5], w[u].z, (unsigned short)0x3c00); fma_h2(acc0[6], acc0[7], w[u].w, (unsigned short)0x3c00);
+                fma_h2(acc1[0], acc1[1], w[2 + u].x, (unsigned short)0x3c00); fma_h2(acc1[2], acc1[3], w[2 + u].y, (unsigned short)0x3c00);
+                fma_h2(acc1[4], acc1[5], w[2 + u].z, (unsigned short)0x3c00); fma_h2(acc1[6], acc1[7], w[2 + u].w, (unsigned short)0x3c00);
             }
+            for (int i = 0; i < cnt; i += 2) {                   // shared rows, two in flight, added to both views
+                const int2 ix = *reinterpret_cast<const int2 *>(wl + i);
+                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.x * kHid2));
+                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(el + (unsigned)ix.y * kHid2));
+                fma_h2(acc0[0], acc0[1], s0.x, (unsigned short)0x3c00); fma_h2(acc0[2], acc0[3], s0.y, (unsigned short)0x3c00);
+                fma_h2(acc0[4], acc0[5], s0.z, (unsigned short)0x3c00); fma_h2(acc0[6], acc0[7], s0.w, (unsigned short)0x3c00);
+                fma_h2(acc1[0], acc1[1], s0.x, (unsigned short)0x3c00); fma_h2(acc1[2], acc1[3], s0.y, (unsigned short)0x3c00);
+                fma_h2(acc1[4], acc1[5], s0.z, (unsigned short)0x3c00); fma_h2(acc1[6], acc1[7], s0.w, (unsigned short)0x3c00);
+                if (i + 1 < cnt) {
+                    fma_h2(acc0[0], acc0[1], s1.x, (unsigned short)0x3c00); fma_h2(acc0[2], acc0[3], s1.y, (unsigned short)0x3c00);
+                    fma_h2(acc0[4], acc0[5], s1.z, (unsigned short)0x3c00); fma_h2(acc0[6], acc0[7], s1.w, (unsigned short)0x3c00);
+                    fma_h2(acc1[0], acc1[1], s1.x, (unsigned short)0x3c00); fma_h2(acc1[2], acc1[3], s1.y, (unsigned short)0x3c00);
+                    fma_h2(acc1[4], acc1[5], s1.z, (unsigned short)0x3c00); fma_h2(acc1[6], acc1[7], s1.w, (unsigned short)0x3c00);
+                }
+            }
+            __syncwarp();
+            finish_row(e_l, acc0);
+            finish_row(ept + e_l, acc1);
         }
-        __syncwarp();
-        finish_row(row_l, acc);
     };
 
     auto do_row = [&](uint4 (&pf)[PLA], const long long tile, const int rr) {
@@ -588,8 +621,14 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
     auto do_finish = [&](const long long tile) {
         constexpr int NA = OC_POLICY_MAX_ACTIONS / TPR;
         const int row_l = tid / TPR, s4 = tid % TPR;
-        const long long row = (long long)tile * p.rpt + row_l;
-        const bool live = row_l < p.rpt && row < p.M;
+        long long row = (long long)tile * p.rpt + row_l;
+        bool live = row_l < p.rpt && row < p.M;
+        if (PL == 0) {       // compact source: tile rows are (view, env-in-tile); global rows are agent-major
+            const int ept = p.rpt >> 1, view = row_l >= ept ? 1 : 0;
+            const long long env = (long long)tile * ept + (row_l - view * ept);
+            row = view * p.N + env;
+            live = row_l < p.rpt && env < p.N;
+        }
         const int A = p.A;
         float l[NA];
 #pragma unroll
@@ -635,8 +674,8 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
                 do_row(pfA, tile, rr);
                 do_row(pfB, tile, rr + 1);
             } else {
-                do_row_cells(cbA, tile, rr);
-                do_row_cells(cbB, tile, rr + 1);
+                do_env_cells(cbA, tile, rr);
+                do_env_cells(cbB, tile, rr + 1);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -948,8 +987,8 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     k.w1 = p->w1; k.w2img = p->w2img; k.small = p->small; k.tmpl = p->tmpl;
     k.M = M; k.N = N; k.K = p->K; k.A = p->A; k.part = p->part;
     k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
-    k.rpt = rows_per_tile(M, p->num_sms);
-    k.n_tiles = (int)((M + k.rpt - 1) / k.rpt);
+    k.rpt = rows_per_tile(M, p->num_sms);                      // a tile holds rpt / 2 envs, both views
+    k.n_tiles = (int)((N + k.rpt / 2 - 1) / (k.rpt / 2));
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     k.cells = cells; k.emb = p->emb; k.scan_cells = p->scan_cells;
     k.cell_stride = p->layout->cell_stride; k.cell_agents = p->layout->cell_agents; k.n_scan = p->layout->host.n_scan;
