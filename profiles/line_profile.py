@@ -5,7 +5,8 @@ import csv, io, re, subprocess, sys, tempfile, os, glob, collections
 rep, lib, ksub = sys.argv[1:4]; ntop = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-dis = subprocess.run(["nvdisasm", "-g", "-c", glob.glob(tmp + "/*.cubin")[0]], capture_output=True, text=True).stdout
+dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", c], capture_output=True, text=True).stdout
+                for c in sorted(glob.glob(tmp + "/*.cubin")))      # one cubin per translation unit
 # instruction order -> (line, inlined-from chain ignored)
 lines = []; cur = None; inside = False
 for l in dis.splitlines():
