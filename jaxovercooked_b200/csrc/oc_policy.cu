@@ -50,7 +50,7 @@ constexpr int kTmemCols = 512;               // two accumulator buffers of 256 c
 struct PolicySmall {
     float base[kHid2];          // Dense_0/Dense_3 bias + template . kernel
     float b2[kHid2];            // Dense_1 | Dense_4 bias
-    float hw[kHid * 8];         // Dense_2 kernel, row c = 8 floats (A used, rest 0)
+    float hw[kHid * 8];         // Dense_2 kernel, row c = 8 floats (A used, rest 0; with A <= 6 slot 6 holds b2[c])
     float cw[kHid];             // Dense_5 kernel
     float b3[8];                // Dense_2 bias (padded)
     float b3c;                  // Dense_5 bias
@@ -583,20 +583,38 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
         const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(buf * kHid2 + net * kHid + part * GC);
         if (net == 0) {
             float pa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.A <= 6) {      // the usual case (Overcooked: 6 actions): row c of hw is {w[c][0..5], b2[c], 0}
 #pragma unroll 1
-            for (int cc = 0; cc < GC / 16; ++cc) {
-                float v[16];
-                tmem_ld16(taddr + cc * 16, v);
+                for (int cc = 0; cc < GC / 16; ++cc) {
+                    float v[16];
+                    tmem_ld16(taddr + cc * 16, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = part * GC + cc * 16 + i;
-                    const float h = activate<ACT>(v[i] + sS->b2[c]);
-                    const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
-                    const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
-                    pa[0] = fmaf(h, wlo.x, pa[0]); pa[1] = fmaf(h, wlo.y, pa[1]);
-                    pa[2] = fmaf(h, wlo.z, pa[2]); pa[3] = fmaf(h, wlo.w, pa[3]);
-                    pa[4] = fmaf(h, whi.x, pa[4]); pa[5] = fmaf(h, whi.y, pa[5]);
-                    pa[6] = fmaf(h, whi.z, pa[6]); pa[7] = fmaf(h, whi.w, pa[7]);
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = part * GC + cc * 16 + i;
+                        const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
+                        const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
+                        const float h = activate<ACT>(v[i] + whi.z);
+                        pa[0] = fmaf(h, wlo.x, pa[0]); pa[1] = fmaf(h, wlo.y, pa[1]);
+                        pa[2] = fmaf(h, wlo.z, pa[2]); pa[3] = fmaf(h, wlo.w, pa[3]);
+                        pa[4] = fmaf(h, whi.x, pa[4]); pa[5] = fmaf(h, whi.y, pa[5]);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int cc = 0; cc < GC / 16; ++cc) {
+                    float v[16];
+                    tmem_ld16(taddr + cc * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = part * GC + cc * 16 + i;
+                        const float h = activate<ACT>(v[i] + sS->b2[c]);
+                        const float4 wlo = *reinterpret_cast<const float4 *>(sS->hw + 8 * c);
+                        const float4 whi = *reinterpret_cast<const float4 *>(sS->hw + 8 * c + 4);
+                        pa[0] = fmaf(h, wlo.x, pa[0]); pa[1] = fmaf(h, wlo.y, pa[1]);
+                        pa[2] = fmaf(h, wlo.z, pa[2]); pa[3] = fmaf(h, wlo.w, pa[3]);
+                        pa[4] = fmaf(h, whi.x, pa[4]); pa[5] = fmaf(h, whi.y, pa[5]);
+                        pa[6] = fmaf(h, whi.z, pa[6]); pa[7] = fmaf(h, whi.w, pa[7]);
+                    }
                 }
             }
             float4 *o = reinterpret_cast<float4 *>(hpA + (row_l * NG + part) * 8);
@@ -754,7 +772,8 @@ __global__ void oc_policy_pack_kernel(const PackArgs a) {
         }
         for (int i = threadIdx.x; i < kHid * 8; i += blockDim.x) {
             const int c = i >> 3, q = i & 7;
-            a.small->hw[i] = q < a.A ? a.kernel[2][(size_t)c * a.A + q] : 0.f;
+            // up to 6 actions: slot 6 of the row carries the layer-2 bias of hidden unit c (one shared-memory read less per column)
+            a.small->hw[i] = q < a.A ? a.kernel[2][(size_t)c * a.A + q] : (q == 6 && a.A <= 6) ? a.bias[1][c] : 0.f;
         }
         for (int c = threadIdx.x; c < kHid; c += blockDim.x) a.small->cw[c] = a.kernel[5][c];
         if (threadIdx.x < 8) a.small->b3[threadIdx.x] = threadIdx.x < a.A ? a.bias[2][threadIdx.x] : 0.f;
