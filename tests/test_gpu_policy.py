@@ -427,3 +427,21 @@ def test_other_action_counts(A, impl):
         clear = (top2[:, 1] - top2[:, 0]) > 1e-5
         np.testing.assert_array_equal(a[clear], a_ref[clear])
     np.testing.assert_allclose(log_prob.cpu().numpy(), po.log_prob(logits.cpu().numpy(), a), atol=3e-6)
+
+
+def test_policy_rollout_sees_parameter_updates():
+    """An optimiser step between two rollouts (in-place update of the parameter tensors) is repacked before the graph replays."""
+    n, T = 128, 4
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"])
+    net = ActorCritic(6)
+    params = po.make_params(8, 520)
+    P = net.params_from_numpy(params)
+    rng = jr.PRNGKey(1)
+    _, state = env.reset(jr.split(rng, n))
+    ro = ocb.PolicyRollout(env, net, P, state, rng, T)
+    ro.run()
+    with torch.no_grad():
+        P["params"]["Dense_5"]["bias"].add_(2.0)
+    ro.run()
+    lo, vo = po.forward(params, ro.transition_obs()[0].cpu().numpy())
+    np.testing.assert_allclose(ro.value[0].cpu().numpy(), vo + 2.0, atol=TOL * max(1.0, np.abs(vo).max() + 2.0))
