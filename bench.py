@@ -46,7 +46,14 @@ def parse():
     ap.add_argument("--random-reset", action="store_true")
     ap.add_argument("--max-steps", type=int, default=400)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--e2e-steps", type=int, default=16000)
+    ap.add_argument("--e2e-steps", type=int, default=4000,
+                    help="steps of the end-to-end leg (host buffers through the C ABI); raised to 2000 unless --min-ms 0; 0 skips the leg")
+    ap.add_argument("--min-ms", type=float, default=250.0,
+                    help="floor of the device-timed window: the 16-step graph is replayed until the CUDA-event window is at least "
+                         "this long, whatever --steps says (the line reports the steps actually timed); 0 = exactly --steps")
+    ap.add_argument("--no-stats-window", action="store_true",
+                    help="skip the LogWrapper-fused window whose int64[8] statistics are all-reduced over the ranks")
+    ap.add_argument("--stats-steps", type=int, default=448)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
@@ -103,10 +110,18 @@ def profiled_traffic(layout_name):
 
 # ------------------------------------------------------------------------------------------- CPU arm
 
+def host_threads():
+    """Host threads this process may use: its CPU affinity mask (a launcher can narrow it), else the core count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_rate(lay, args, n_envs, seconds, threads=None, steps=None):
     """env-steps/s of the oracle (OpenMP over envs) on the host cores."""
     from oracle import oracle as orc
-    orc.set_threads(threads or os.cpu_count() or 1)
+    orc.set_threads(threads or host_threads())
     cores = orc.max_threads()
     o = orc.Oracle(lay, random_reset=args.random_reset, max_steps=args.max_steps)
     rng = np.random.default_rng(0)
@@ -133,12 +148,61 @@ def cpu_rate(lay, args, n_envs, seconds, threads=None, steps=None):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on this box's host cores.
+
+    1. If a real `jax` and the reference tree (baseline/_ref or /root/reference) are importable: the reference's
+       jitted, vmapped step in a lax.scan on JAX_PLATFORMS=cpu (baseline/ref_jax.py; kind "reference-jax-cpu").
+    2. Otherwise (this image: no jax wheel, no network): the C restatement oracle/oc_oracle.c with OpenMP (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
     lay = get_layout(args)
-    orc.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the other ranks do no work
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        time.sleep(5.0)                    # let the other (idle) ranks of the torchrun job import, see their rank and exit
+    line = None
+    try:
+        from baseline import ref_jax
+        if ref_jax.available():
+            line = run_reference_jax(args, lay, ref_jax)
+    except Exception as ex:                # a broken JAX install must not take the arm down: fall back to the port, say why
+        print(f"reference arm: real-JAX path failed ({type(ex).__name__}: {ex}); timing the C port instead", file=sys.stderr)
+        line = None
+    if line is None:
+        line = run_reference_port(args, lay)
+    print(json.dumps(line), flush=True)
+
+
+def reference_line(args, lay, value, steps, warmup, ms_per_step, n_envs, cores, kind, sample):
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args, lay), "sample_envs_per_step": n_envs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def run_reference_jax(args, lay, ref_jax):
+    jax = ref_jax.import_jax()
+    ns = ref_jax.load_reference()
+    cores = host_threads()
+    steps = max(1, args.steps)
+    # bounded sample: a pilot at 1,024 envs sizes the batch so that warm-up + 3 timed runs of `steps` steps take about a minute
+    pilot, _, _ = ref_jax.time_random_rollout(jax, ns, lay, args.layout, n_envs=1024, n_steps=8, random_reset=args.random_reset,
+                                              max_steps=args.max_steps, repeats=1)
+    n_envs = int(min(args.envs, max(256, pilot * 15.0 / steps)))
+    n_envs = max(256, (n_envs // 256) * 256)
+    value, best, compile_s = ref_jax.time_random_rollout(jax, ns, lay, args.layout, n_envs=n_envs, n_steps=steps,
+                                                         random_reset=args.random_reset, max_steps=args.max_steps, repeats=3)
+    sample = (f"{n_envs} of {args.envs} envs per step x {steps} steps, best of 3 after one compile+warm-up run ({compile_s:.1f} s): "
+              f"the reference's own jax.jit(jax.vmap(env.step)) in a lax.scan (jax {jax.__version__}, JAX_PLATFORMS=cpu, "
+              f"{cores} host threads available)")
+    return reference_line(args, lay, value, steps, steps, best / steps * 1e3, n_envs, cores, "reference-jax-cpu", sample)
+
+
+def run_reference_port(args, lay):
+    from oracle import oracle as orc
+    orc.set_threads(host_threads())        # torchrun exports OMP_NUM_THREADS=1; the other ranks do no work
     cores = orc.max_threads()
     # bounded sample: size each step so that warmup + K steps finish in about a minute
     probe, _, _, _ = cpu_rate(lay, args, 8192, 1.0)
@@ -161,15 +225,9 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n_envs * args.steps / dt
     sample = (f"{n_envs} of {args.envs} envs per step x {args.steps} steps, C restatement of the reference "
-              f"(oracle/oc_oracle.c, OpenMP, {cores} threads); the reference's own JAX path cannot be installed here")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(args, lay), "sample_envs_per_step": n_envs},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+              f"(oracle/oc_oracle.c, OpenMP, {cores} threads); the reference's own JAX path cannot be installed here "
+              f"(no jax wheel in the image; bench.py picks it up through baseline/ref_jax.py wherever `import jax` works)")
+    return reference_line(args, lay, value, args.steps, max(3, args.warmup), dt / args.steps * 1e3, n_envs, cores, "port", sample)
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -230,6 +288,89 @@ class ClockSampler:
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- statistics window
+
+STATS_SPLIT_NUM = 1 << 23     # per-env keys are split(key, 2**23)[global env index]: the same for any number of GPUs
+
+
+def stats_window(args, env, dev, world, rank, N):
+    """A LogWrapper-fused window whose exact integer statistics (oc_step_extras.stats) are reduced over the ranks: the one
+    collective of this path (the reference's `tree_map(mean)` over rollout info, baselines/IPPO_CL.py:771-812).
+
+    Every environment's trajectory here depends only on its GLOBAL index (reset key, per-step key and actions are functions of
+    the global index), so rank 0's shard is the same whatever the world size, and the all-reduced vector must equal the sum
+    of the per-rank vectors gathered separately."""
+    import torch
+    import torch.distributed as dist
+    import jaxovercooked_b200 as ocb
+    from jaxovercooked_b200 import random as ocr
+    from jaxovercooked_b200.dist import reduce_stats, stats_to_metrics
+    T = max(1, args.stats_steps)
+    first = rank * N
+    wenv = ocb.LogWrapper(env)
+    ks = ocr.split(ocr.PRNGKey(777), 2)
+    _, st = wenv.reset(ocr.split(ks[1], STATS_SPLIT_NUM, first=first, count=N))
+    subs = ocr.split_chain(ks[0].clone(), T)
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    h, w = env.height, env.width
+    out = {"obs0": torch.empty((N, h, w, 26), dtype=torch.uint8, device=dev),
+           "obs1": torch.empty((N, h, w, 26), dtype=torch.uint8, device=dev),
+           "reward": torch.empty(N, dtype=torch.float32, device=dev), "shaped0": torch.empty(N, dtype=torch.float32, device=dev),
+           "shaped1": torch.empty(N, dtype=torch.float32, device=dev), "done": torch.empty(N, dtype=torch.bool, device=dev)}
+    gidx = torch.arange(first, first + N, dtype=torch.int64, device=dev)
+
+    def actions(t):   # a fixed integer hash of (step, global env index): uniform-looking, world-size independent
+        x = (gidx * 0x9E3779B1 + (t + 1) * 0x85EBCA6B) & 0xFFFFFFFF
+        x = ((x ^ (x >> 15)) * 0x2C1B3C6D) & 0xFFFFFFFF
+        x = ((x ^ (x >> 12)) * 0x297A2D39) & 0xFFFFFFFF
+        x = x ^ (x >> 15)
+        return {"agent_0": (x % 6).to(torch.int32), "agent_1": ((x >> 8) % 6).to(torch.int32)}
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for t in range(T):
+        _, st, _, _, _ = wenv.step(ocr.LazySplit(subs[t], STATS_SPLIT_NUM, first, N), st, actions(t), donate=True, out=out,
+                                   stats=stats)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    shard = stats.clone()
+    res = {"steps": T, "envs_per_gpu": N, "global_envs": N * world, "launches": T,
+           "eager_ms": ms, "keys_and_actions": "functions of the global env index (split(key, 2**23)[i]; integer hash of (t, i))",
+           "stats_names": ["finished_episodes", "sum_reward", "sum_shaped_agent_0", "sum_shaped_agent_1",
+                           "sum_returned_episode_returns", "sum_returned_episode_lengths", "env_steps", "reserved"]}
+    if world > 1:
+        gathered = [torch.zeros_like(shard) for _ in range(world)]
+        dist.all_gather(gathered, shard)
+        warm = torch.zeros(8, dtype=torch.int64, device=dev)
+        reduce_stats(warm)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0.record()
+        reduce_stats(stats)                      # the collective itself: one NCCL all-reduce of int64[8]
+        ev1.record()
+        torch.cuda.synchronize()
+        first_us = ev0.elapsed_time(ev1) * 1e3
+        reps = 50
+        ev0.record()
+        for _ in range(reps):
+            reduce_stats(warm)
+        ev1.record()
+        torch.cuda.synchronize()
+        per_rank = [g.cpu().tolist() for g in gathered]
+        total = [sum(v[i] for v in per_rank) for i in range(8)]
+        res.update({"stats_allreduced": stats.cpu().tolist(), "stats_shard0": per_rank[0],
+                    "allreduce_equals_sum_of_shards": total == stats.cpu().tolist(),
+                    "allreduce_us": first_us, "allreduce_us_avg50": ev0.elapsed_time(ev1) * 1e3 / reps,
+                    "backend": "nccl int64[8] sum"})
+    else:
+        res.update({"stats_allreduced": shard.cpu().tolist(), "stats_shard0": shard.cpu().tolist(),
+                    "allreduce_equals_sum_of_shards": True, "allreduce_us": None, "backend": "single rank: no collective"})
+    res["metrics"] = stats_to_metrics(torch.tensor(res["stats_allreduced"]))
+    return res
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -366,7 +507,7 @@ def run_ours(args):
     BLOCK = 2 * GRAPH_STEPS
     K = max(BLOCK, (args.steps // BLOCK) * BLOCK)
     Wm = max(3, args.warmup)
-    n_warm_blocks = (Wm + BLOCK - 1) // BLOCK
+    n_warm_blocks = max(2, (Wm + BLOCK - 1) // BLOCK)
     stream = torch.cuda.Stream(dev)
     with torch.cuda.stream(stream):
         generate(0)
@@ -378,8 +519,20 @@ def run_ours(args):
             with torch.cuda.graph(graph, stream=stream):
                 block(1)
         run_blocks = (lambda n: [graph.replay() for _ in range(n)]) if graph is not None else block
+        evw0, evw1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        run_blocks(1)
+        evw0.record(stream)
         run_blocks(n_warm_blocks)
+        evw1.record(stream)
         torch.cuda.synchronize()
+        # time floor: however few steps were asked for, the timed window is at least --min-ms long (same count on every rank)
+        n_blocks = K // BLOCK
+        if args.min_ms > 0:
+            est = torch.tensor([evw0.elapsed_time(evw1) / n_warm_blocks], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(est, op=dist.ReduceOp.MIN)
+            n_blocks = max(n_blocks, int(np.ceil(args.min_ms / max(float(est.item()), 1e-3))))
+        K = n_blocks * BLOCK
         if world > 1:
             dist.barrier()
         sampler = ClockSampler(local)
@@ -396,6 +549,9 @@ def run_ours(args):
         ms = ev0.elapsed_time(ev1)
         if stats is not None and world > 1:
             dist.all_reduce(stats)     # the rollout statistics: the only collective on this path
+    stats_win = None
+    if not args.no_stats_window and not args.policy:
+        stats_win = stats_window(args, env, dev, world, rank, N)
 
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -403,15 +559,15 @@ def run_ours(args):
     ms = float(tmax.item())
     value = n_global * K / (ms * 1e-3)
     launches_per_block = (2 if args.policy else 1) * BLOCK + 2   # our kernels: 16 steps (+ 16 policy forwards) + 2 key-chain kernels (the 2 RNG kernels are torch's)
-    gpu_launches = (K // BLOCK) * launches_per_block
+    gpu_launches = (K // BLOCK) * launches_per_block + (stats_win["launches"] if stats_win else 0)
 
     # ---- e2e: the C-ABI call with HOST buffers (oc_step_host through env.host_stepper): every step copies that
     # step's actions from pinned host memory to the device and the step's rewards / shaped rewards / dones back to
     # pinned host memory.  The R env batches run on R streams, so one batch's copies overlap another's kernel; the
     # host waits for a batch's previous results before it reuses that batch's buffers.
     e2e = None
-    if not args.log_wrapper and not args.policy:
-        Ke = max(2 * R, min(args.e2e_steps, max(args.steps, 2 * R)))
+    if not args.log_wrapper and not args.policy and args.e2e_steps > 0:
+        Ke = max(2 * R, args.e2e_steps if args.min_ms <= 0 else max(args.e2e_steps, 2000))
         torch.cuda.synchronize()
         steppers = [env.host_stepper(states[b], n_global, first) for b in range(R)]
         h_pool = [torch.randint(0, 6, (2, N), dtype=torch.int32).pin_memory() for _ in range(16)]
@@ -457,12 +613,13 @@ def run_ours(args):
                 "peak_source": peak_src}
     cpu = None
     if world == 1 and not args.no_cpu and not args.policy:
-        n_cpu = min(N, 16384)
+        n_cpu = N          # the same batch the reference arm (`--impl reference`) steps
         v, cores, n_steps, dt = cpu_rate(lay, args, n_cpu, args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_cpu} envs x {n_steps} steps in {dt:.1f} s, oracle/oc_oracle.c (C restatement, OpenMP); "
                          "the reference's JAX CPU path is not installable in this image"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": n_warm_blocks * BLOCK,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": (n_warm_blocks + 2) * BLOCK,
+            "requested_steps": args.steps, "replays": K // BLOCK, "timed_window_ms": ms,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": workload_name(args, lay), "envs_per_gpu": N, "global_envs": n_global,
@@ -484,6 +641,9 @@ def run_ours(args):
         line["config"]["policy_input"] = args.policy_input
     if stats is not None:
         line["stats"] = stats.cpu().tolist()
+    if stats_win is not None:
+        stats_win.pop("launches", None)
+        line["stats_window"] = stats_win
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -107,12 +107,12 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w;
-    kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = lay->tmpl_smem_bytes;
+    kp.n_scan = H.n_scan; kp.prev_bytes = (lay->epw * H.n_scan + 15) & ~15;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
     kp.pf_bytes = lay->pf_bytes;
     kp.pf_invariant = (((long long)lay->epw * H.map_bytes) % 16 == 0 && (long long)lay->epw * H.map_bytes + 32 < 65536) ? 1 : 0;
-    kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
+    kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1));
     kp.cell_stride = lay->cell_stride; kp.cell_agents = lay->cell_agents;
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
@@ -141,7 +141,14 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
         const long long k = (want + resident - 1) / resident;
         ctas = (want + k - 1) / k;
     }
+    if (const char *ev = std::getenv("OC_B200_MAX_CTAS")) {   // tests: force many tiles per warp on small batches
+        const long long v = std::atoll(ev);
+        if (v >= 1 && v < ctas) ctas = v;
+    }
     static const bool use_pdl = [] { const char *e = std::getenv("OC_B200_PDL"); return !(e && e[0] == '0'); }();
+    static const int dbg = [] { const char *e = std::getenv("OC_B200_DBG"); return e ? std::atoi(e) : 0; }();
+    static const int stagger = [] { const char *e = std::getenv("OC_B200_STAGGER_NS"); return e ? std::atoi(e) : 0; }();
+    kp.dbg = dbg; kp.stagger_ns = (unsigned)stagger;
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);
@@ -303,9 +310,12 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
     auto pf_bytes_for = [&](int e) { return ((e * (L.span_stride / 16) * 4) + 15) & ~15; };
-    const int tmpl_smem = (L.tmpl_chunks * 16 <= 4096) ? L.tmpl_chunks * 16 : 0;
-    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + tmpl_smem;
-    auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15; };
+    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15);
+    const int views = OC_TWO_VIEWS ? 2 : 1;
+    // per warp: staging image(s) | 2 span buffers | urgency flags | staged scan codes
+    auto warp_bytes_for = [&](int e) {
+        return ((views * e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + e * 4 + ((e * L.n_scan + 15) & ~15)) + 15) & ~15;
+    };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     // (warps per CTA, envs per warp).  Resident warps per SM are limited by shared memory and by the 64 registers x
     // 1024 threads the kernel is compiled for.  Measured on B200: beyond ~24 resident warps more warps stop paying,
@@ -329,16 +339,19 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
             else better = warps > best || (warps == best && (e > epw || (e == epw && wv > W)));
             if (!epw || better) { best = warps; best_enough = enough; epw = e; W = wv; }
         }
+    if (const char *ev = std::getenv("OC_B200_WARPS")) {   // tuning
+        const int v = std::atoi(ev);
+        if (v >= 1 && v <= kWarpsPerCta) W = v;
+    }
     if (const char *ev = std::getenv("OC_B200_EPW")) {
         const int v = std::atoi(ev);
-        if ((v == 2 || v == 4 || v == 8 || v == 16) && size_ok(v) &&
+        if (v >= 2 && v <= 16 && size_ok(v) &&
             kHdrBytesHost0 + pf_bytes_for(v) + W * warp_bytes_for(v) <= smem_cap) epw = v;
     }
     if (!epw) { delete lay; return OC_ERR_UNSUPPORTED_LAYOUT; }
     lay->epw = epw;
     lay->warp_bytes = warp_bytes_for(epw);
     lay->pf_bytes = pf_bytes_for(epw);
-    lay->tmpl_smem_bytes = tmpl_smem;
     lay->warps = W;
     lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + W * lay->warp_bytes;
     lay->num_sms = prop.multiProcessorCount;

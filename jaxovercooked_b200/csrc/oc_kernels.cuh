@@ -11,7 +11,7 @@ namespace {
 // CELLS: also emit the compact form of the observations (oc_step_extras.cells); a separate instantiation so that the
 // plain kernel keeps its register budget
 template <int MODE, bool CELLS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
     // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
@@ -22,9 +22,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + kHdrFixed);   // [n_scan] span offset | cell << 16
     uint32_t *s_pf = reinterpret_cast<uint32_t *>(smem + kHdrFixed + p.scan_bytes);   // [epw*nch] prefetch plan
-    // small static images are kept in shared memory and copied by the lanes (tmpl_bytes > 0); large ones are pulled
-    // per tile from global memory by the bulk-copy engine
-    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed + p.scan_bytes + p.pf_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
@@ -33,31 +30,55 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     const int part = p.part;
     const int env_bytes = C * OC_OBS_CHANNELS;
     const int view_bytes = epw * env_bytes;
-    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.pf_bytes + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
+    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.pf_bytes + (size_t)warp * p.warp_bytes;
+    // The warp's staging image of a tile's observations is PERSISTENT: it is filled with the layout's static image once
+    // per launch, and from then on every tile only re-writes what can differ from it -- the scan cells whose code
+    // changed against the previous tile in the same slot, the two agent cells (un-patched to the floor's all-zero
+    // record before the next tile), and the urgency plane of slots whose flag flipped.
     unsigned char *stage = wbase;                                              // agent_0's view of the tile
+#if OC_TWO_VIEWS
+    unsigned char *stage1 = wbase + view_bytes;                                // agent_1's view, same life cycle
+    unsigned char *smap_buf = wbase + 2 * view_bytes;                          // 2 x [epw][span_stride]
+#else
     unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
-    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] urgency flags
-    const uint32_t tbar = smem_u32(s_ap + 2 * epw);                                    // this warp's mbarrier (8 bytes)
+#endif
+    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [epw] urgency flags
+    unsigned char *s_prev = reinterpret_cast<unsigned char *>(s_ap + epw);         // [epw*n_scan] staged scan codes
     unsigned char *s_cells = wbase + p.cells_off;        // CELLS: [epw][cell_stride] staging of the compact observations
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
     bool bulk_pending = false;
-    // agent_1's view differs from agent_0's only in the two agent cells (overcooked.py:356-359): the staged image is
-    // sent to obs0, then -- as soon as the copy engine has READ it -- the two agent cells are re-staged from
-    // agent_1's perspective and the same buffer is sent to obs1.
-    // write one cell's 26-byte record into the staged image at flat cell index g (2-byte aligned offset g*26)
-    auto stage_record = [&](int g, int code) {
+    // agent_1's view differs from agent_0's only in the two agent cells (overcooked.py:356-359).  With one staging
+    // image: it is sent to obs0, then -- as soon as the copy engine has READ it -- the two agent cells are re-staged
+    // from agent_1's perspective and the same buffer is sent to obs1.  With OC_TWO_VIEWS each view has its own image
+    // and both copies are issued back to back.
+    // write one cell's 26-byte record into a staged image at flat cell index g (2-byte aligned offset g*26); `urg`
+    // is channel 25 (the urgency plane, :311,:341; every record of the table has it clear)
+    auto stage_record = [&](unsigned char *img, int g, int code, uint32_t urg) {
         const uint32_t *r = g_rec + code * kRecWords + ((g & 1) ? 8 : 0);
         const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(r)), v1 = __ldg(reinterpret_cast<const uint4 *>(r + 4));
-        unsigned char *dst = stage + g * OC_OBS_CHANNELS;
+        unsigned char *dst = img + g * OC_OBS_CHANNELS;
         if (g & 1) {   // offset = 2 (mod 4): shifted record -- upper half of word 0, then words 1..6
             *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(v0.x >> 16);
             uint32_t *d = reinterpret_cast<uint32_t *>(dst + 2);
-            d[0] = v0.y; d[1] = v0.z; d[2] = v0.w; d[3] = v1.x; d[4] = v1.y; d[5] = v1.z;
+            d[0] = v0.y; d[1] = v0.z; d[2] = v0.w; d[3] = v1.x; d[4] = v1.y; d[5] = v1.z | (urg << 24);
         } else {       // word aligned: words 0..5, then the lower half of word 6
             uint32_t *d = reinterpret_cast<uint32_t *>(dst);
             d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y;
-            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)(v1.z & 0xffffu);
+            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)((v1.z & 0xffffu) | (urg << 8));
+        }
+    };
+    // agents only ever stand on floor cells, whose record is all zero: un-patching an agent cell needs no table
+    auto stage_floor = [&](unsigned char *img, int g, uint32_t urg) {
+        unsigned char *dst = img + g * OC_OBS_CHANNELS;
+        if (g & 1) {
+            *reinterpret_cast<unsigned short *>(dst) = 0;
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst + 2);
+            d[0] = 0u; d[1] = 0u; d[2] = 0u; d[3] = 0u; d[4] = 0u; d[5] = urg << 24;
+        } else {
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+            d[0] = 0u; d[1] = 0u; d[2] = 0u; d[3] = 0u; d[4] = 0u; d[5] = 0u;
+            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)(urg << 8);
         }
     };
 
@@ -118,9 +139,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     // wait for the previous kernel's memory to be visible before touching any environment state.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     {
-        if (p.tmpl_bytes) {
-            const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
-            for (int i = tid; i < p.tmpl_chunks; i += cta_threads) s_tmpl[i] = __ldg(tsrc + i);
+        {   // static image of a whole tile (L2-resident, 16-byte aligned) -> this warp's staging image(s)
+            const uint4 *tsrc = reinterpret_cast<const uint4 *>(p.tmpl_tile);
+            for (int f = lane; f < (view_bytes >> 4); f += 32) {
+                const uint4 v = __ldg(tsrc + f);
+                reinterpret_cast<uint4 *>(stage)[f] = v;
+#if OC_TWO_VIEWS
+                reinterpret_cast<uint4 *>(stage1)[f] = v;
+#endif
+            }
+            for (int i = lane; i < (p.prev_bytes >> 2); i += 32) reinterpret_cast<uint32_t *>(s_prev)[i] = 0xffffffffu;
         }
         for (int i = tid; i < p.n_scan; i += cta_threads) s_scan[i] = L->scan[i];
         if (p.pf_invariant) {
@@ -138,14 +166,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
         if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
     }
-    // The static observation image of a tile lives in global memory (L2-resident, tile-sized); each tile's staging
-    // buffer is (re)filled from it by ONE bulk asynchronous copy that completes on this warp's mbarrier while the
-    // step logic runs.
-    uint32_t tphase = 0;
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tbar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (CELLS)         // padding bytes of the compact form stay 0xFF
         for (int i = lane; i < (epw * p.cell_stride) >> 2; i += 32) reinterpret_cast<uint32_t *>(s_cells)[i] = 0xffffffffu;
     __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
@@ -153,7 +173,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
     long long tile = (long long)blockIdx.x * cta_warps + warp;
     int buf = 0;
     Fields nf;
+    int prev_cell = -1, surg = 0;   // what this lane left in the staging image: its agent cell, its slot's urgency flag
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
+    if (p.stagger_ns && (warp & 1)) {   // tuning probe: de-phase the two halves of the CTA's warps
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do { __nanosleep(200); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < p.stagger_ns);
+    }
 
     for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
         const long long env0 = tile * epw;
@@ -168,16 +194,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         unsigned char *my_span = smap + es * span_stride + ((m0 + es * p.map_bytes) & 15);
         unsigned char *g_span = g_tile + es * p.map_bytes;                                   // same bytes in HBM
 
-        // ------------------------------------------------ (0) refill the staging buffer with the static image
-        if (!p.tmpl_bytes) {
-            if (lane == 0) {
-                if (bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // obs1 of the previous tile
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tbar), "r"(view_bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(stage)), "l"(p.tmpl_tile), "r"(view_bytes), "r"(tbar) : "memory");
-            }
-            bulk_pending = false;
-        }
         // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
         const Fields cf = nf;
         if (tile + tile_stride < p.n_tiles) {
@@ -359,38 +375,43 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
 
         // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
         bool obs1_pending = false;
-        int code_v1 = 0, my_cell = 0, urg_lane = 0;
+        int code_v1 = 0, my_cell = 0;
         const size_t obs_off = (size_t)env0 * env_bytes;
+        const uint32_t urg = (uint32_t)((p.max_steps - t_out) < 40);                          // :311
         {
-            const int urg = (p.max_steps - t_out) < 40;                                       // :311
-            if (active) s_ap[lane] = (uint32_t)urg;
-            // (4a) base image
-            if (p.tmpl_bytes) {   // copied by the lanes from shared memory, 16 bytes per lane-step
-                if (bulk_pending) {   // the previous tile's obs1 copy must have finished READING the staging buffer
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    bulk_pending = false;
-                    __syncwarp();
-                }
-                const int n_chunks = (n_valid * env_bytes + 15) >> 4;
-                uint4 *dst = reinterpret_cast<uint4 *>(stage);
-                int src = lane;                                                         // tiles start on a template period
-                src -= (int)fastdiv((unsigned)src, p.magic_tc) * p.tmpl_chunks;
-                const int step = 32 - (int)fastdiv(32u, p.magic_tc) * p.tmpl_chunks;      // 32 mod tmpl_chunks
-                for (int f = lane; f < n_chunks; f += 32) {
-                    dst[f] = s_tmpl[src];
-                    src += step;
-                    if (src >= p.tmpl_chunks) src -= p.tmpl_chunks;
-                }
-            } else {              // wait for the bulk copy issued at the top of the tile
-                uint32_t ok = 0;
-                while (!ok) {
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(tbar), "r"(tphase) : "memory");
-                }
-                tphase ^= 1u;
+            if (active && ai == 0) s_ap[e] = urg;
+            if (bulk_pending) {   // the previous tile's copies must have finished READING the staging image(s)
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bulk_pending = false;
             }
             __syncwarp();
-            // (4b) cells that can deviate from the base image: counters next to a walkable cell (loose items) and pots
+            // (4a) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left -- only slots whose
+            // flag differs from what the image holds are touched
+            {
+                const unsigned chg = __ballot_sync(0xffffffffu, active && ai == 0 && (int)urg != surg);
+                if (chg) {
+                    const int n_cells = n_valid * C;
+                    for (int g = lane; g < n_cells; g += 32) {
+                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
+                        if ((chg >> (2 * el)) & 1u) {
+                            stage[g * OC_OBS_CHANNELS + 25] = (unsigned char)s_ap[el];
+#if OC_TWO_VIEWS
+                            stage1[g * OC_OBS_CHANNELS + 25] = (unsigned char)s_ap[el];
+#endif
+                        }
+                    }
+                }
+                if (active) surg = (int)urg;
+            }
+            // (4b) the cell this lane's agent occupied in the previous tile of this slot goes back to the floor record
+            if (active && prev_cell >= 0) {
+                stage_floor(stage, prev_cell, urg);
+#if OC_TWO_VIEWS
+                stage_floor(stage1, prev_cell, urg);
+#endif
+            }
+            // (4c) cells that can deviate from the static image: counters next to a walkable cell (loose items) and pots;
+            // re-staged only where the code differs from what the previous tile left in this slot
             {
                 const int total = n_valid * p.n_scan;
                 for (int f = lane; f < total; f += 32) {
@@ -398,16 +419,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                     const uint32_t sc = s_scan[f - el * p.n_scan];
                     const unsigned char *c = smap + el * span_stride + ((m0 + el * p.map_bytes) & 15) + (int)(sc & 0xffffu);
                     const int o = c[0], st = c[2];
-                    if (o == 8 ? (st != 23) : (o != 2 && o != 10))
-                        stage_record(el * C + (int)(sc >> 16), (o == 8) ? kCodePot + min(st, 23) : min(o, 10));
+                    const int code = (o == 8) ? kCodePot + min(st, 23) : min(o, 10);
+                    if (s_prev[f] != code) {
+                        s_prev[f] = (unsigned char)code;
+                        stage_record(stage, el * C + (int)(sc >> 16), code, s_ap[el]);
+#if OC_TWO_VIEWS
+                        stage_record(stage1, el * C + (int)(sc >> 16), code, s_ap[el]);
+#endif
+                    }
                     if (CELLS)     // the compact form of this observation (include/oc_b200.h, oc_step_extras.cells)
                         s_cells[el * p.cell_stride + (f - el * p.n_scan)] =
-                            (uint8_t)((o == 8 ? (st != 23) : (o != 2 && o != 10)) ? ((o == 8) ? kCodePot + min(st, 23) : min(o, 10)) : 0xff);
+                            (uint8_t)((o == 8 ? (st != 23) : (o != 2 && o != 10)) ? code : 0xff);
                 }
             }
             __syncwarp();
-            // (4c) agent cells show the agent, its direction and what it holds (:313-323, :345-353)
-            if (active) stage_record(es * C + ny * w + nx, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)));
+            // (4d) agent cells show the agent, its direction and what it holds (:313-323, :345-353); agent_1 sees the
+            // same cell with "which" flipped (it is the viewer)
+            my_cell = es * C + ny * w + nx;
+            code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
+            if (active) {
+                stage_record(stage, my_cell, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)), urg);
+#if OC_TWO_VIEWS
+                stage_record(stage1, my_cell, code_v1, urg);
+#endif
+                prev_cell = my_cell;
+            }
             if (CELLS) {
                 if (active) {
                     unsigned char *cl = s_cells + es * p.cell_stride + p.cell_agents;
@@ -421,31 +457,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                 uint4 *dst = reinterpret_cast<uint4 *>(p.cells + env0 * p.cell_stride);
                 for (int i = lane; i < (n_valid * p.cell_stride) >> 4; i += 32) dst[i] = src[i];
             }
-            __syncwarp();
-            // (4d) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left
-            {
-                const unsigned urg_mask = __ballot_sync(0xffffffffu, active && urg && ai == 0);
-                if (urg_mask) {
-                    const int n_cells = n_valid * C;
-                    for (int g = lane; g < n_cells; g += 32) {
-                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
-                        if (s_ap[2 * el]) stage[g * OC_OBS_CHANNELS + 25] = 1;
-                    }
-                }
-            }
-            // this lane's agent cell as agent_1 sees it: "which" flipped (agent_1 is the viewer)
-            code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
-            my_cell = es * C + ny * w + nx;
-            urg_lane = urg;
             if (p.bulk_ok && n_valid == epw) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(p.dbg & 1)) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
+#if OC_TWO_VIEWS
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage1)), "r"(view_bytes) : "memory");
+#endif
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+#if OC_TWO_VIEWS
+                bulk_pending = true;
+#else
                 obs1_pending = true;      // issued after the state write-back below, which hides the engine's read
+#endif
             } else {
                 // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular
                 __syncwarp();
@@ -454,11 +482,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
                 unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + obs_off);
                 unsigned short *g1 = reinterpret_cast<unsigned short *>(p.obs1 + obs_off);
                 for (int k = lane; k < (nb >> 1); k += 32) g0[k] = h0[k];
+#if OC_TWO_VIEWS
+                const unsigned short *h1 = reinterpret_cast<const unsigned short *>(stage1);
+                for (int k = lane; k < (nb >> 1); k += 32) g1[k] = h1[k];
+#else
                 __syncwarp();
-                if (active) stage_record(my_cell, code_v1);
-                if (urg && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
+                if (active) stage_record(stage, my_cell, code_v1, urg);
                 __syncwarp();
                 for (int k = lane; k < (nb >> 1); k += 32) g1[k] = h0[k];
+#endif
             }
         }
 
@@ -538,11 +570,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) oc_env_kernel(const __gr
         if (obs1_pending) {   // agent_1's view: re-stage the two agent cells once the engine has read the image
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
-            if (active) stage_record(my_cell, code_v1);
-            if (urg_lane && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
+            if (active) stage_record(stage, my_cell, code_v1, urg);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.dbg & 1)) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");

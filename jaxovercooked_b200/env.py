@@ -178,6 +178,40 @@ class Overcooked:
             setattr(sp, f, t.data_ptr())
         return sp
 
+    def _check(self, t, what, dtypes, shape):
+        """The kernels write through raw pointers: a wrong dtype, shape, device or a non-contiguous view would corrupt
+        memory silently, so every caller-provided buffer is checked before its address crosses the C ABI."""
+        dtypes = dtypes if isinstance(dtypes, tuple) else (dtypes,)
+        if (not torch.is_tensor(t) or t.dtype not in dtypes or tuple(t.shape) != tuple(shape) or not t.is_contiguous()
+                or t.device != self.device):
+            got = f"{t.dtype}{list(t.shape)} on {t.device}, contiguous={t.is_contiguous()}" if torch.is_tensor(t) else type(t).__name__
+            raise ValueError(f"{what}: expected a contiguous {' or '.join(str(d) for d in dtypes)}{list(shape)} tensor on "
+                             f"{self.device}, got {got}")
+        return t
+
+    def _check_out(self, out, batch):
+        b = tuple(batch)
+        img = b + (self.height, self.width, N_CHANNELS)
+        self._check(out["obs0"], "out['obs0']", torch.uint8, img)
+        self._check(out["obs1"], "out['obs1']", torch.uint8, img)
+        for k in ("reward", "shaped0", "shaped1"):
+            self._check(out[k], f"out['{k}']", torch.float32, b)
+        self._check(out["done"], "out['done']", (torch.bool, torch.uint8), b)
+        if out.get("cells") is not None:
+            self._check(out["cells"], "out['cells']", torch.uint8, b + (self.info.cell_stride,))
+
+    def _check_log(self, log, stats, batch):
+        b2 = tuple(batch) + (self.num_agents,)
+        if log is not None:
+            for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths"):
+                if log.get(f) is None:
+                    raise ValueError(f"log['{f}'] is missing: the four LogWrapper trackers go together")
+                self._check(log[f], f"log['{f}']", torch.float32, b2)
+            if log.get("returned_episode") is not None:
+                self._check(log["returned_episode"], "log['returned_episode']", (torch.bool, torch.uint8), b2)
+        if stats is not None:
+            self._check(stats, "stats", torch.int64, (8,))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -198,6 +232,8 @@ class Overcooked:
         key = self._key(key)
         batch = tuple(key.shape[:-1])
         n = int(np.prod(batch)) if batch else 1
+        if cells is not None:
+            self._check(cells, "cells", torch.uint8, batch + (self.info.cell_stride,))
         st = self.empty_state(batch)
         obs0, obs1 = self._obs_buffers(batch)
         with torch.cuda.device(self.device):
@@ -242,14 +278,14 @@ class Overcooked:
             sh1 = torch.empty(batch, dtype=torch.float32, device=self.device)
             done = torch.empty(batch, dtype=torch.bool, device=self.device)
         else:
+            self._check_out(out, batch)
             obs0, obs1, reward, sh0, sh1, done = (out[k] for k in ("obs0", "obs1", "reward", "shaped0", "shaped1", "done"))
+        self._check_log(log, stats, batch)
         ex = None
         cells = out.get("cells") if out is not None else None
         if log is not None or stats is not None or lazy is not None or cells is not None:
             e = _lib.StepExtras()
             if cells is not None:
-                if cells.dtype != torch.uint8 or tuple(cells.shape) != tuple(batch) + (self.info.cell_stride,) or not cells.is_contiguous():
-                    raise ValueError(f"out['cells'] must be a contiguous uint8 tensor of shape {tuple(batch) + (self.info.cell_stride,)}")
                 e.cells = cells.data_ptr()
             if lazy is not None:
                 e.split_key, e.split_num, e.split_first = lazy.key.data_ptr(), lazy.num, lazy.first
@@ -281,6 +317,8 @@ class Overcooked:
         """overcooked.py:250-364.  `cells` (uint8 [N, cell_stride]) also receives the compact form."""
         batch = tuple(state.time.shape)
         n = int(np.prod(batch)) if batch else 1
+        if cells is not None:
+            self._check(cells, "cells", torch.uint8, batch + (self.info.cell_stride,))
         obs0, obs1 = self._obs_buffers(batch)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.oc_get_obs_cells(self._handle, n, self._state_ptrs(state, batch), obs0.data_ptr(),
@@ -395,6 +433,11 @@ class HostStepper:
         """Enqueue one step; `key` is the step's subkey (uint32[2] CUDA tensor), split per env inside the kernel.
         `actions`: a pinned int32[2,N] host tensor to use instead of `self.actions` (no host-side copy)."""
         act = self.actions if actions is None else actions
+        if actions is not None and (not torch.is_tensor(act) or act.dtype != torch.int32 or tuple(act.shape) != (2, self.n)
+                                    or not act.is_contiguous() or act.device.type != "cpu" or not act.is_pinned()):
+            raise ValueError(f"actions must be a contiguous pinned int32 host tensor of shape (2, {self.n})")
+        if not torch.is_tensor(key) or key.dtype != torch.uint32 or tuple(key.shape) != (2,) or key.device != self.env.device:
+            raise ValueError("key must be a uint32[2] tensor on the env's device (the step's subkey)")
         self._keepalive = (key, act)
         rc = self._step(self._h, key.data_ptr(), act.data_ptr())
         if rc:

@@ -137,20 +137,48 @@ def _struct_dataclass(cls):
 # ---------------------------------------------------------------------------------------------- vmap
 
 def _vmap(fn, in_axes=0, out_axes=0):
-    """Eager loop over the mapped axis (axis 0 only, which is all the reference uses)."""
+    """Eager loop over the mapped axis (axis 0 only, which is all the reference uses); arguments may be pytrees."""
+    def leaves(t):
+        out = []
+        tree_map(lambda x: out.append(x), t)
+        return out
+
     def mapped(*args):
         axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
         n = None
         for a, ax in zip(args, axes):
             if ax is not None:
                 assert ax == 0
-                n = len(a)
+                n = len(leaves(a)[0])
         outs = []
         for i in range(n):
-            call = [_wrap(np.asarray(a)[i]) if ax is not None else a for a, ax in zip(args, axes)]
+            call = [tree_map(lambda x: _wrap(np.asarray(x)[i]), a) if ax is not None else a for a, ax in zip(args, axes)]
             outs.append(fn(*call))
         return tree_map(lambda *xs: _stack(xs), outs[0], *outs[1:])
     return mapped
+
+
+def _scan(f, init, xs=None, length=None):
+    """jax.lax.scan, eagerly."""
+    if xs is None:
+        n = length
+    else:
+        first = []
+        tree_map(lambda a: first.append(a), xs)
+        n = len(first[0])
+    carry, ys = init, []
+    for i in range(n):
+        x = None if xs is None else tree_map(lambda a: _wrap(np.asarray(a)[i]), xs)
+        carry, y = f(carry, x)
+        ys.append(y)
+    return carry, tree_map(lambda *v: _stack(v), ys[0], *ys[1:])
+
+
+class _Config:
+    @staticmethod
+    def update(name, value):
+        if name == "jax_threefry_partitionable":
+            _Cfg.partitionable = bool(value)
 
 
 def _jit(fn=None, static_argnums=None, **_):
@@ -263,6 +291,7 @@ def install(partitionable=False):
     lax = types.ModuleType("jax.lax")
     lax.select = lambda pred, a, b: _wrap(np.where(np.asarray(pred), a, b))
     lax.stop_gradient = lambda x: x
+    lax.scan = _scan
 
     rnd = types.ModuleType("jax.random")
     rnd.PRNGKey = lambda seed: _prng.PRNGKey(seed).view(Arr)
@@ -279,6 +308,8 @@ def install(partitionable=False):
     jax.numpy, jax.lax, jax.random, jax.tree = jnp, lax, rnd, tree
     jax.vmap = _vmap
     jax.jit = _jit
+    jax.config = _Config
+    jax.block_until_ready = lambda x: x
     jax.tree_map = tree_map
 
     chex = types.ModuleType("chex")

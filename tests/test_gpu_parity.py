@@ -67,7 +67,8 @@ def test_cuda_matches_reference_golden(case):
             assert_same(info["returned_episode"].cpu().numpy(), g["lw_returned_episode"][t], f"t={t} returned_episode")
 
 
-def _rollout_compare(lay, *, random_reset, max_steps, N, T, seed, part=False, every=1, donate=True, log=False):
+def _rollout_compare(lay, *, random_reset, max_steps, N, T, seed, part=False, every=1, donate=True, log=False,
+                     time_offsets=False):
     ocb, orc, gh = _mods()
     from oracle import prng
     env = ocb.make("overcooked", layout=lay, random_reset=random_reset, max_steps=max_steps,
@@ -82,6 +83,10 @@ def _rollout_compare(lay, *, random_reset, max_steps, N, T, seed, part=False, ev
     assert_same(obs["agent_0"].cpu().numpy(), r0, "reset obs0")
     assert_same(obs["agent_1"].cpu().numpy(), r1, "reset obs1")
     gh.compare_state(st.env_state if log else st, rst, "reset")
+    if time_offsets:     # envs at different points of their episodes: urgency and resets hit different slots of a tile
+        off = rng.integers(0, max_steps, N).astype(np.int32)
+        rst["time"][:] = off
+        (st.env_state if log else st).time.copy_(gh.to_dev(off))
     for t in range(T):
         sk = rng.integers(0, 2**32, (N, 2), dtype=np.uint32)
         a = rng.choice(6, size=(N, 2), p=ACTION_P).astype(np.int32)
@@ -113,6 +118,21 @@ def test_all_layouts_vs_oracle(name, random_reset):
     from jaxovercooked_b200.layouts import overcooked_layouts
     _rollout_compare(overcooked_layouts[name], random_reset=random_reset, max_steps=17, N=203, T=40,
                      seed=hash(name) % 1000 + int(random_reset), every=3)
+
+
+@pytest.mark.parametrize("max_ctas", ["1", "3"])
+@pytest.mark.parametrize("name,random_reset", [("cramped_room", False), ("cramped_room", True), ("coord_ring", True),
+                                               ("counter_circuit", False), ("bottleneck_large", True),
+                                               ("easy_layout_padded", False)])
+def test_many_tiles_per_warp(name, random_reset, max_ctas, monkeypatch):
+    """The warp's staging image of the observations persists from tile to tile (only what differs from the static
+    image is re-written, and un-written for the next tile).  Small batches give every warp at most one tile, so this
+    caps the grid (OC_B200_MAX_CTAS) to push dozens of tiles through each warp, with per-env episode phases mixed so
+    that urgency flags and auto-resets differ between the tiles that reuse a staging slot."""
+    from jaxovercooked_b200.layouts import overcooked_layouts
+    monkeypatch.setenv("OC_B200_MAX_CTAS", max_ctas)
+    _rollout_compare(overcooked_layouts[name], random_reset=random_reset, max_steps=61, N=777, T=90,
+                     seed=7 + int(max_ctas), every=2, time_offsets=True, log=(max_ctas == "3"))
 
 
 @pytest.mark.parametrize("part", [False, True])
@@ -486,3 +506,51 @@ def test_unaligned_observation_buffers_take_the_plain_store_path():
         _, st_a, _, _, _ = env.step(ocr.LazySplit(subs[t], N), st_a, a, donate=True, out=out)
         obs, st_b, *_ = env.step(ocr.LazySplit(subs[t], N), st_b, a, donate=True)
         assert torch.equal(o0, obs["agent_0"]) and torch.equal(o1, obs["agent_1"])
+
+
+def test_caller_buffers_are_validated_before_they_cross_the_abi():
+    """Raw pointers go to the kernels: wrong dtype / shape / device / non-contiguous buffers must raise, not corrupt memory."""
+    ocb, orc, gh = _mods()
+    from jaxovercooked_b200 import random as ocr
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"])
+    N = 12
+    keys = ocr.split(ocr.PRNGKey(0), N)
+    _, st = env.reset(keys)
+    act = {"agent_0": torch.zeros(N, dtype=torch.int32, device="cuda"), "agent_1": torch.zeros(N, dtype=torch.int32, device="cuda")}
+
+    def good():
+        return {"obs0": torch.empty((N, 4, 5, 26), dtype=torch.uint8, device="cuda"),
+                "obs1": torch.empty((N, 4, 5, 26), dtype=torch.uint8, device="cuda"),
+                "reward": torch.empty(N, dtype=torch.float32, device="cuda"), "shaped0": torch.empty(N, dtype=torch.float32, device="cuda"),
+                "shaped1": torch.empty(N, dtype=torch.float32, device="cuda"), "done": torch.empty(N, dtype=torch.bool, device="cuda")}
+    env.step(keys, st, act, out=good())
+    bad = [("reward", torch.empty(N, dtype=torch.float64, device="cuda")),
+           ("obs0", torch.empty((N, 4, 5, 26), dtype=torch.bool, device="cuda")),
+           ("obs1", torch.empty((N, 5, 4, 26), dtype=torch.uint8, device="cuda")),
+           ("obs0", torch.empty((2 * N, 4, 5, 26), dtype=torch.uint8, device="cuda")[::2]),
+           ("done", torch.empty(N, dtype=torch.int32, device="cuda")),
+           ("shaped1", torch.empty(N, dtype=torch.float32)),
+           ("shaped0", torch.empty(N + 1, dtype=torch.float32, device="cuda"))]
+    for k, t in bad:
+        o = good()
+        o[k] = t
+        with pytest.raises(ValueError):
+            env.step(keys, st, act, out=o)
+    z = lambda: torch.zeros((N, 2), dtype=torch.float32, device="cuda")
+    log = {"episode_returns": z(), "episode_lengths": z(), "returned_episode_returns": z(), "returned_episode_lengths": z()}
+    env.step(keys, st, act, log=dict(log), stats=torch.zeros(8, dtype=torch.int64, device="cuda"))
+    with pytest.raises(ValueError):
+        env.step(keys, st, act, log=dict(log, episode_lengths=torch.zeros(N, dtype=torch.float32, device="cuda")))
+    with pytest.raises(ValueError):
+        env.step(keys, st, act, log={k: v for k, v in log.items() if k != "episode_returns"})
+    with pytest.raises(ValueError):
+        env.step(keys, st, act, stats=torch.zeros(8, dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        env.step(keys, st, act, stats=torch.zeros(4, dtype=torch.int64, device="cuda"))
+    hs = env.host_stepper(st)
+    with pytest.raises(ValueError):
+        hs.step(ocr.PRNGKey(1), torch.zeros((2, N), dtype=torch.int32))           # not pinned
+    with pytest.raises(ValueError):
+        hs.step(ocr.PRNGKey(1), torch.zeros((N, 2), dtype=torch.int32).pin_memory())
+    hs.step(ocr.PRNGKey(1), torch.zeros((2, N), dtype=torch.int32).pin_memory())
+    hs.wait()
