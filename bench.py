@@ -54,6 +54,12 @@ def parse():
     ap.add_argument("--no-stats-window", action="store_true",
                     help="skip the LogWrapper-fused window whose int64[8] statistics are all-reduced over the ranks")
     ap.add_argument("--stats-steps", type=int, default=448)
+    ap.add_argument("--rollout-steps", type=int, default=16,
+                    help="steps per launch: oc_rollout keeps the environments on chip for this many steps (the callers' lax.scan "
+                         "over env.step with the actions given); 0 = one oc_step launch per step in a replayed CUDA graph")
+    ap.add_argument("--e2e-wire", default="reference", choices=["reference", "packed"],
+                    help="host wire format of the e2e leg: the reference's dtypes (int32 actions, float32 results: 21 B per "
+                         "env-step) or the packed one (2 B per env-step); the other one is reported next to it")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--log-wrapper", action="store_true", help="fuse the LogWrapper + statistics epilogue")
@@ -386,7 +392,19 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pinned_cores = None
     if world > 1:
+        # one process per GPU on one host: give every rank its own slice of the host cores, so that eight Python loops and
+        # their CUDA driver threads do not migrate over each other (the e2e leg is host-driven)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            per = len(cores) // max(1, lw)
+            if per >= 1:
+                pinned_cores = cores[local * per:(local + 1) * per]
+                os.sched_setaffinity(0, pinned_cores)
+        except Exception:
+            pinned_cores = None
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
@@ -460,7 +478,39 @@ def run_ours(args):
         oclib.check(lib.oc_prng_chain(env.prng_mode, chain_rng.data_ptr(), KPS * GRAPH_STEPS, subkeys[hf].data_ptr(),
                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "oc_prng_chain")
 
+    RO = args.rollout_steps if (args.rollout_steps > 0 and not args.policy and not args.emit_cells and args.streams == 1) else 0
+    if RO:
+        # oc_rollout: ONE launch steps a batch RO times.  Each half has its own action block [2, RO, N] and subkeys [RO, 2]
+        # (re-drawn on the side stream while the other half runs) and its own trajectory buffers: observations in the
+        # learners' layout uint8[RO, 2, N, h, w, 26] (1.09 GB per half at 65,536 envs x 16 steps: far larger than L2)
+        ro_act = torch.zeros((2, 2, RO, N), dtype=torch.int32, device=dev)
+        ro_keys = torch.zeros((2, RO, 2), dtype=torch.uint32, device=dev)
+        n_ro_bufs = 2 if 2 * RO * 2 * N * h * w * 26 > 300e6 else 4
+        ro_out = [{"obs": torch.empty((RO, 2, N, h, w, 26), dtype=torch.uint8, device=dev),
+                   "reward": torch.empty((RO, N), dtype=torch.float32, device=dev),
+                   "shaped0": torch.empty((RO, N), dtype=torch.float32, device=dev),
+                   "shaped1": torch.empty((RO, N), dtype=torch.float32, device=dev),
+                   "done": torch.empty((RO, N), dtype=torch.bool, device=dev)} for _ in range(n_ro_bufs)]
+
+        def generate(hf):   # noqa: F811 -- the rollout form of the generator above
+            ro_act[hf].random_(0, 6)
+            oclib.check(lib.oc_prng_chain(env.prng_mode, chain_rng.data_ptr(), RO, ro_keys[hf].data_ptr(),
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "oc_prng_chain")
+
     step_no = [0]
+
+    def one_rollout(hf):
+        j = step_no[0]
+        step_no[0] += 1
+        b = j % R
+        st_b = states[b]
+        log = None
+        if args.log_wrapper:
+            log = {f: getattr(st_b, f) for f in ("episode_returns", "episode_lengths", "returned_episode_returns",
+                                                 "returned_episode_lengths")}
+            st_b = st_b.env_state
+        env.rollout((ro_keys[hf], n_global, first), st_b, {"agent_0": ro_act[hf, 0], "agent_1": ro_act[hf, 1]},
+                    out=ro_out[j % n_ro_bufs], log=log, stats=stats if args.log_wrapper else None)
 
     def one_step(hf, i):
         j = step_no[0]
@@ -493,7 +543,9 @@ def run_ours(args):
                     generate(1 - hf)
                 for st_ in extra:
                     st_.wait_stream(main)
-                for i in range(GRAPH_STEPS):
+                if RO:
+                    one_rollout(hf)
+                for i in range(0 if RO else GRAPH_STEPS):
                     lane_ = i % args.streams        # --streams > 1: independent env batches advance concurrently
                     if lane_ == 0:
                         one_step(hf, i)
@@ -504,7 +556,7 @@ def run_ours(args):
                     main.wait_stream(st_)
                 main.wait_stream(side)
 
-    BLOCK = 2 * GRAPH_STEPS
+    BLOCK = 2 * (RO if RO else GRAPH_STEPS)
     K = max(BLOCK, (args.steps // BLOCK) * BLOCK)
     Wm = max(3, args.warmup)
     n_warm_blocks = max(2, (Wm + BLOCK - 1) // BLOCK)
@@ -558,7 +610,7 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = n_global * K / (ms * 1e-3)
-    launches_per_block = (2 if args.policy else 1) * BLOCK + 2   # our kernels: 16 steps (+ 16 policy forwards) + 2 key-chain kernels (the 2 RNG kernels are torch's)
+    launches_per_block = ((2 if args.policy else 1) * BLOCK + 2) if not RO else 4   # rollout mode: 2 oc_rollout + 2 key-chain kernels   # our kernels: 16 steps (+ 16 policy forwards) + 2 key-chain kernels (the 2 RNG kernels are torch's)
     gpu_launches = (K // BLOCK) * launches_per_block + (stats_win["launches"] if stats_win else 0)
 
     # ---- e2e: the C-ABI call with HOST buffers (oc_step_host through env.host_stepper): every step copies that
@@ -566,7 +618,60 @@ def run_ours(args):
     # pinned host memory.  The R env batches run on R streams, so one batch's copies overlap another's kernel; the
     # host waits for a batch's previous results before it reuses that batch's buffers.
     e2e = None
-    if not args.log_wrapper and not args.policy and args.e2e_steps > 0:
+    if RO and not args.log_wrapper and args.e2e_steps > 0:
+        # ---- e2e, rollout form: oc_rollout_host through env.HostRollout.  Per RO steps of a batch: ONE host-to-device copy of
+        # the RO steps' actions from pinned host memory, one launch, ONE device-to-host copy of the RO steps' rewards / shaped
+        # rewards / dones into pinned host memory; the R env batches run on R streams.  Measured for both wire formats.
+        Ke = max(2 * R * RO, args.e2e_steps if args.min_ms <= 0 else max(args.e2e_steps, 2000))
+        n_ro = (Ke + RO - 1) // RO
+        n_ro = ((n_ro + R - 1) // R) * R
+        Ke = n_ro * RO
+        torch.cuda.synchronize()
+        e_keys = ocr.split_chain(rngs[1 % R], (n_ro + 2 * R) * RO).view(n_ro + 2 * R, RO, 2)
+        res_e2e = {}
+        for wire in ("reference", "packed"):
+            packed = wire == "packed"
+            # the trajectory buffers of the device-timed leg are reused (each HostRollout writes a [RO, 2, N, ...] buffer)
+            hrs = [ocb.HostRollout(env, states[b], RO, n_global, first, packed=packed, obs=ro_out[b % n_ro_bufs]["obs"]) for b in range(R)]
+            if packed:
+                h_pool = [(torch.randint(0, 6, (RO, N)) | (torch.randint(0, 6, (RO, N)) << 4)).to(torch.uint8).pin_memory() for _ in range(4)]
+            else:
+                h_pool = [torch.randint(0, 6, (2, RO, N), dtype=torch.int32).pin_memory() for _ in range(4)]
+            torch.cuda.synchronize()
+
+            def e2e_run(i0, n):
+                for i in range(i0, i0 + n):
+                    hr = hrs[i % R]
+                    hr.wait()                                    # this batch's previous results are on the host
+                    hr.run(e_keys[i], h_pool[i % 4])
+
+            e2e_run(0, 2 * R)
+            for hr in hrs:
+                hr.wait()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            e2e_run(2 * R, n_ro)
+            for hr in hrs:
+                hr.wait()
+            dt = time.perf_counter() - t0
+            tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            res_e2e[wire] = n_global * Ke / float(tm.item())
+            del hrs
+        wire = args.e2e_wire
+        other = "packed" if wire == "reference" else "reference"
+        bi, bo = (N, N) if wire == "packed" else (8 * N, 13 * N)
+        e2e = {"value": res_e2e[wire], "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "steps": Ke,
+               "wire": wire, f"value_{other}_wire": res_e2e[other],
+               f"bytes_per_env_step_{other}_wire": 2 if other == "packed" else 21,
+               "host_calls": n_ro, "steps_per_host_call": RO, "pinned_cores": len(pinned_cores) if pinned_cores else None,
+               "note": f"oc_rollout_host (C ABI, host buffers) via env.HostRollout: per {RO} steps of a batch one copy of the "
+                       "actions from pinned host memory in, one launch, one copy of rewards+shaped+dones to pinned host memory "
+                       "out (those bytes are counted per step); observations stay on the device for the learner, as in the "
+                       f"reference; {R} env batches pipelined on {R} streams"}
+    elif not args.log_wrapper and not args.policy and args.e2e_steps > 0:
         Ke = max(2 * R, args.e2e_steps if args.min_ms <= 0 else max(args.e2e_steps, 2000))
         torch.cuda.synchronize()
         steppers = [env.host_stepper(states[b], n_global, first) for b in range(R)]
@@ -611,6 +716,16 @@ def run_ours(args):
                 "traffic": profiled_traffic(args.layout), "kernel": "oc_env_kernel<MODE_STEP>",
                 "algorithmic_bytes_per_env_step": B_alg, "envs_per_launch": N, "avg_launch_us": step_s * 1e6,
                 "peak_source": peak_src}
+    if RO:
+        # one launch = N envs x RO steps.  `achieved` follows SURVEY.md 8(d)'s per-env-step figure (state in + state out + both
+        # observations + keys/actions/results per step); the rollout kernel itself needs fewer bytes -- the state crosses HBM
+        # once per RO steps -- and that smaller figure is reported next to it
+        hw_ = h * w
+        b_kernel = 52 * hw_ + 21 + (6 * hw_ + 82) / RO
+        roofline.update({"kernel": "oc_env_kernel<MODE_ROLLOUT>", "env_steps_per_launch": N * RO, "steps_per_launch": RO,
+                         "avg_launch_us": step_s * 1e6 * RO, "traffic": None,
+                         "kernel_bytes_per_env_step": b_kernel, "achieved_kernel_bytes": b_kernel * N / step_s / 1e9,
+                         "frac_kernel_bytes": b_kernel * N / step_s / 1e9 / peak})
     cpu = None
     if world == 1 and not args.no_cpu and not args.policy:
         n_cpu = N          # the same batch the reference arm (`--impl reference`) steps
@@ -623,13 +738,19 @@ def run_ours(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": workload_name(args, lay), "envs_per_gpu": N, "global_envs": n_global,
-                       "l2": f"inputs larger than L2: {R} independent env batches + {OBS_SLOTS} observation slots "
-                             f"round-robin (state {R * N * (env.info.map_bytes_per_env + 41) / 1e6:.0f} MB + obs "
-                             f"{OBS_SLOTS * 2 * N * h * w * 26 / 1e6:.0f} MB per cycle vs 126 MB L2)",
-                       "launch": "CUDA graph of 16 steps replayed (next 8 steps' actions/subkeys generated on a side branch)"
+                       "l2": (f"inputs larger than L2: {R} independent env batches + {OBS_SLOTS} observation slots "
+                              f"round-robin (state {R * N * (env.info.map_bytes_per_env + 41) / 1e6:.0f} MB + obs "
+                              f"{OBS_SLOTS * 2 * N * h * w * 26 / 1e6:.0f} MB per cycle vs 126 MB L2)") if not RO else
+                             (f"outputs larger than L2: every launch writes a fresh uint8[{RO}, 2, N, h, w, 26] trajectory buffer "
+                              f"({RO * 2 * N * h * w * 26 / 1e6:.0f} MB; {n_ro_bufs} of them round-robin) and steps one of {R} "
+                              f"independent env batches (state {R * N * (env.info.map_bytes_per_env + 41) / 1e6:.0f} MB per cycle) vs 126 MB L2"),
+                       "launch": (f"CUDA graph of 2 oc_rollout launches x {RO} steps replayed (the next {RO} steps' actions/subkeys "
+                                  "generated on a side branch)" if RO else
+                                  "CUDA graph of 16 steps replayed (next 8 steps' actions/subkeys generated on a side branch)")
                                  if graph is not None else "eager launches",
+                       "steps_per_launch": RO if RO else 1,
                        "keys": "per-step subkeys from the split chain; per-env split fused in the kernel",
-                       "actions": "i.i.d. uniform {0..5}, re-drawn on the device every 8 steps inside the timed region",
+                       "actions": f"i.i.d. uniform {{0..5}}, re-drawn on the device every {RO if RO else 8} steps inside the timed region",
                        "concurrent_branches": args.streams, "log_wrapper": bool(args.log_wrapper), "emit_cells": bool(args.emit_cells or args.policy), "parallelism": f"env-sharded x{world}, no per-step comms"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
     if args.policy:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define OC_B200_VERSION 110          /* 0.1.1: + compact observations, oc_policy_* */
+#define OC_B200_VERSION 120          /* 0.1.2: + oc_rollout, oc_rollout_host */
 #define OC_MAX_DIM 16                /* height, width <= 16 (reference registry max: 10 x 11) */
 #define OC_MAX_CELLS 256
 #define OC_MAX_SPECIAL 16            /* pots, goals, onion piles, plate piles: at most 16 each */
@@ -186,6 +186,46 @@ int  oc_host_stepper_step(oc_host_stepper *stepper, const uint32_t *split_key, c
 int  oc_host_stepper_wait(oc_host_stepper *stepper);
 void oc_host_stepper_destroy(oc_host_stepper *stepper);
 
+/* T consecutive env.step calls on the same batch in ONE launch: the callers' `jax.lax.scan(_env_step, ..., length=T)` over
+ * `jax.vmap(env.step)` (baselines/unused/random_actions.py:197-225; baselines/IPPO_CL.py:520-560 with the actions given).
+ * Each warp loads its environments once, keeps them in shared memory and registers for the T steps and writes them back
+ * once, so a step costs no state traffic and no launch: results are bit-identical to T oc_step calls (tests/test_gpu_rollout.py).
+ * Per-step arrays carry a leading T:
+ *   keys            u32[T,N,2], or NULL with extras->split_key = DEVICE u32[T,2]: env i at step t uses
+ *                   jax.random.split(split_key[t], split_num)[split_first + i]
+ *   io->act0/act1   i32[T,N]            (or io->actions8: u8[T,N] = agent_0's action | agent_1's action << 4)
+ *   io->obs0/obs1   step t's observations u8[N,h,w,26] start obs_step_stride BYTES after step t-1's
+ *                   (>= N*h*w*26; e.g. 2*N*h*w*26 with obs1 = obs0 + N*h*w*26 writes the learners' [T,2,N,h,w,26] buffer)
+ *   io->reward/shaped0/shaped1 f32[T,N], io->done u8[T,N]
+ *                   (or io->results8: u8[T,N] = reward/20 | class(shaped0) << 2 | class(shaped1) << 4 | done << 6 with
+ *                    class(0) = 0, class(3) = 1, class(5) = 2 -- the only values the reference produces, overcooked.py:30-35,502)
+ *   extras          LogWrapper trackers [N,2] are read once, updated T times and written once; returned_episode is
+ *                   u8[T,N,2]; cells is u8[T,N,cell_stride]; stats accumulate the T steps.
+ * `state` is stepped in place.  reset_state is not supported here (use oc_step). */
+typedef struct {
+    const int32_t *act0, *act1;
+    const uint8_t *actions8;
+    uint8_t *obs0, *obs1;
+    int64_t obs_step_stride;
+    float *reward, *shaped0, *shaped1;
+    uint8_t *done;
+    uint8_t *results8;
+} oc_rollout_io;
+
+int oc_rollout(const oc_layout *layout, int64_t N, int32_t T, const uint32_t *keys, oc_state state,
+               const oc_rollout_io *io, const oc_step_extras *extras, void *stream);
+
+/* oc_rollout for a caller whose policy lives on the HOST -- the T-step form of oc_step_host: ONE host-to-device copy of
+ * the T steps' actions, one launch, ONE device-to-host copy of the T steps' results, all enqueued on `stream`.
+ *   wire = OC_WIRE_REFERENCE  h_actions HOST i32[2,T,N] (agent-major); h_results HOST 13*T*N bytes:
+ *                             reward f32[T,N] | shaped0 f32[T,N] | shaped1 f32[T,N] | done u8[T,N]; d_scratch 21*T*N bytes
+ *   wire = OC_WIRE_PACKED     h_actions HOST u8[T,N] (actions8); h_results HOST u8[T,N] (results8); d_scratch 2*T*N bytes
+ * d_scratch is DEVICE memory, 16-byte aligned; T*N % 4 == 0.  extras->split_key (DEVICE u32[T,2]) is required. */
+typedef enum { OC_WIRE_REFERENCE = 0, OC_WIRE_PACKED = 1 } oc_wire_format;
+int oc_rollout_host(const oc_layout *layout, int64_t N, int32_t T, oc_state state, int wire, const void *h_actions,
+                    void *h_results, void *d_scratch, uint8_t *obs0, uint8_t *obs1, int64_t obs_step_stride,
+                    const oc_step_extras *extras, void *stream);
+
 /* env.get_obs under vmap: overcooked.py:250-364. */
 int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, void *stream);
 /* ... and their compact form as well (see oc_step_extras.cells): what a rollout needs right after oc_reset. */
@@ -236,7 +276,9 @@ typedef struct {
                                         (oc_layout_obs_template); layer 1 is evaluated as a correction to it.  Any
                                         input is handled correctly with any template -- only the speed depends on it */
     const oc_layout *layout;         /* or NULL.  When given, obs_dim must be h*w*26, the layout's static image is the template
-                                        and oc_policy_forward_cells becomes available; the layout must outlive the policy */
+                                        and oc_policy_forward_cells becomes available.  Everything the policy needs from the layout
+                                        is copied by oc_policy_create (the layout may be destroyed first); it must live on
+                                        the current device (OC_ERR_INVALID_ARG otherwise) */
 } oc_policy_desc;
 
 typedef struct oc_policy oc_policy;  /* opaque: the parameters repacked for the kernels, in device memory */

@@ -10,10 +10,10 @@ missing -- there is no CPU fallback.
 from .layouts import (Layout, overcooked_layouts, layout_grid_to_dict, pad_layouts, cl_sequence_padded,  # noqa: F401
                       hard_layouts, medium_layouts, easy_layouts, padded_layouts)
 
-__version__ = "0.1.1"
+__version__ = "0.1.2"
 
 _LAZY = {"Overcooked": "env", "State": "env", "make": "env", "vmap": "env", "registered_envs": "env",
-         "Actions": "env", "LogWrapper": "wrappers", "LogEnvState": "wrappers", "CTRolloutManager": "wrappers", "random": None, "env": None,
+         "Actions": "env", "HostStepper": "env", "HostRollout": "env", "LogWrapper": "wrappers", "LogEnvState": "wrappers", "CTRolloutManager": "wrappers", "random": None, "env": None,
          "wrappers": None, "dist": None, "rollout": None, "RolloutBuffer": "rollout", "PolicyRollout": "rollout", "policy": None,
          "ActorCritic": "policy"}
 

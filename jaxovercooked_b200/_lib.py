@@ -48,6 +48,15 @@ class LayoutInfo(C.Structure):
                 ("n_scan", C.c_int32), ("cell_stride", C.c_int32), ("cell_agents", C.c_int32)]
 
 
+class RolloutIO(C.Structure):
+    _fields_ = [("act0", C.c_void_p), ("act1", C.c_void_p), ("actions8", C.c_void_p), ("obs0", C.c_void_p),
+                ("obs1", C.c_void_p), ("obs_step_stride", C.c_int64), ("reward", C.c_void_p), ("shaped0", C.c_void_p),
+                ("shaped1", C.c_void_p), ("done", C.c_void_p), ("results8", C.c_void_p)]
+
+
+WIRE_REFERENCE, WIRE_PACKED = 0, 1
+
+
 class PolicyDesc(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("activation", C.c_int32), ("prng_mode", C.c_int32),
                 ("kernel", C.c_void_p * 6), ("bias", C.c_void_p * 6), ("obs_template", C.c_void_p),
@@ -55,7 +64,7 @@ class PolicyDesc(C.Structure):
 
 
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
-           "oc_reset", "oc_step", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
+           "oc_reset", "oc_step", "oc_rollout", "oc_rollout_host", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
            "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_prng_split", "oc_prng_chain",
            "oc_policy_create", "oc_policy_update", "oc_policy_destroy", "oc_policy_forward", "oc_policy_forward_cells", "oc_policy_sample",
            "oc_layout_obs_template", "oc_get_obs_cells", "oc_layout_cell_tables")
@@ -96,6 +105,12 @@ def load():
     lib.oc_step.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p,
                             C.POINTER(StatePtrs), StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.POINTER(StepExtras), C.c_void_p]
+    lib.oc_rollout.restype = C.c_int
+    lib.oc_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, StatePtrs, C.POINTER(RolloutIO),
+                               C.POINTER(StepExtras), C.c_void_p]
+    lib.oc_rollout_host.restype = C.c_int
+    lib.oc_rollout_host.argtypes = [C.c_void_p, C.c_int64, C.c_int32, StatePtrs, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(StepExtras), C.c_void_p]
     lib.oc_step_host.restype = C.c_int
     lib.oc_step_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.POINTER(StepExtras), C.c_void_p]

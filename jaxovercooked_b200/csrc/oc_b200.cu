@@ -107,12 +107,12 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
     kp.agent_cell0 = H.agent_cell[0]; kp.agent_cell1 = H.agent_cell[1];
     kp.magic_C = H.magic_C; kp.magic_w = H.magic_w;
-    kp.n_scan = H.n_scan; kp.prev_bytes = (lay->epw * H.n_scan + 15) & ~15;
+    kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = lay->tmpl_smem_bytes;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
     kp.pf_bytes = lay->pf_bytes;
     kp.pf_invariant = (((long long)lay->epw * H.map_bytes) % 16 == 0 && (long long)lay->epw * H.map_bytes + 32 < 65536) ? 1 : 0;
-    kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1));
+    kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.cell_stride = lay->cell_stride; kp.cell_agents = lay->cell_agents;
     kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
     if (kp.n_tiles < 1) return OC_OK;
@@ -125,30 +125,23 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     if (smem_bytes > 227 * 1024) return OC_ERR_UNSUPPORTED_LAYOUT;
     kp.cells_off = lay->warp_bytes;
     kp.warp_bytes = lay->warp_bytes + cells_smem;
-    if (lay->occ[MODE + (with_cells ? 3 : 0)] == 0) {
+    if (lay->occ[MODE + (with_cells ? NUM_MODES : 0)] == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, smem_bytes) != cudaSuccess)
             return fail_cuda();
-        lay->occ[MODE + (with_cells ? 3 : 0)] = nb < 1 ? 1 : nb;
+        lay->occ[MODE + (with_cells ? NUM_MODES : 0)] = nb < 1 ? 1 : nb;
     }
     // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
-    const long long resident = (long long)lay->num_sms * lay->occ[MODE + (with_cells ? 3 : 0)];
+    const long long resident = (long long)lay->num_sms * lay->occ[MODE + (with_cells ? NUM_MODES : 0)];
     const long long want = (kp.n_tiles + lay->warps - 1) / lay->warps;
     long long ctas = want;
     if (want > resident) {
         const long long k = (want + resident - 1) / resident;
         ctas = (want + k - 1) / k;
     }
-    if (const char *ev = std::getenv("OC_B200_MAX_CTAS")) {   // tests: force many tiles per warp on small batches
-        const long long v = std::atoll(ev);
-        if (v >= 1 && v < ctas) ctas = v;
-    }
     static const bool use_pdl = [] { const char *e = std::getenv("OC_B200_PDL"); return !(e && e[0] == '0'); }();
-    static const int dbg = [] { const char *e = std::getenv("OC_B200_DBG"); return e ? std::atoi(e) : 0; }();
-    static const int stagger = [] { const char *e = std::getenv("OC_B200_STAGGER_NS"); return e ? std::atoi(e) : 0; }();
-    kp.dbg = dbg; kp.stagger_ns = (unsigned)stagger;
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);
@@ -310,12 +303,9 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
     auto pf_bytes_for = [&](int e) { return ((e * (L.span_stride / 16) * 4) + 15) & ~15; };
-    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15);
-    const int views = OC_TWO_VIEWS ? 2 : 1;
-    // per warp: staging image(s) | 2 span buffers | urgency flags | staged scan codes
-    auto warp_bytes_for = [&](int e) {
-        return ((views * e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + e * 4 + ((e * L.n_scan + 15) & ~15)) + 15) & ~15;
-    };
+    const int tmpl_smem = (L.tmpl_chunks * 16 <= 4096) ? L.tmpl_chunks * 16 : 0;
+    const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + tmpl_smem;
+    auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
     // (warps per CTA, envs per warp).  Resident warps per SM are limited by shared memory and by the 64 registers x
     // 1024 threads the kernel is compiled for.  Measured on B200: beyond ~24 resident warps more warps stop paying,
@@ -339,25 +329,22 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
             else better = warps > best || (warps == best && (e > epw || (e == epw && wv > W)));
             if (!epw || better) { best = warps; best_enough = enough; epw = e; W = wv; }
         }
-    if (const char *ev = std::getenv("OC_B200_WARPS")) {   // tuning
-        const int v = std::atoi(ev);
-        if (v >= 1 && v <= kWarpsPerCta) W = v;
-    }
     if (const char *ev = std::getenv("OC_B200_EPW")) {
         const int v = std::atoi(ev);
-        if (v >= 2 && v <= 16 && size_ok(v) &&
+        if ((v == 2 || v == 4 || v == 8 || v == 16) && size_ok(v) &&
             kHdrBytesHost0 + pf_bytes_for(v) + W * warp_bytes_for(v) <= smem_cap) epw = v;
     }
     if (!epw) { delete lay; return OC_ERR_UNSUPPORTED_LAYOUT; }
     lay->epw = epw;
     lay->warp_bytes = warp_bytes_for(epw);
     lay->pf_bytes = pf_bytes_for(epw);
+    lay->tmpl_smem_bytes = tmpl_smem;
     lay->warps = W;
     lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + W * lay->warp_bytes;
     lay->num_sms = prop.multiProcessorCount;
     lay->cell_agents = (L.n_scan + 1) & ~1;
     lay->cell_stride = (lay->cell_agents + 5 + 15) & ~15;
-    for (int i = 0; i < 6; ++i) lay->occ[i] = 0;
+    for (int i = 0; i < 2 * NUM_MODES; ++i) lay->occ[i] = 0;
     lay->device = device;
     {   // tile-sized static observation image
         const size_t eb = (size_t)C * OC_OBS_CHANNELS;
@@ -371,7 +358,7 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     }
     if (cudaMalloc(&lay->dev, sizeof(DevLayout)) != cudaSuccess) { cudaFree(lay->tmpl_tile); delete lay; return fail_cuda(); }
     if (cudaMemcpy(lay->dev, &L, sizeof(DevLayout), cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaFree(lay->dev); delete lay; return fail_cuda();
+        cudaFree(lay->dev); cudaFree(lay->tmpl_tile); delete lay; return fail_cuda();
     }
     *out = lay;
     return OC_OK;
@@ -504,6 +491,69 @@ int oc_step_host(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state
                            d_res + 2 * N, reinterpret_cast<uint8_t *>(d_res + 3 * N), extras, stream_);
     if (rc != OC_OK) return rc;
     if (cudaMemcpyAsync(h_results, d_res, (size_t)13 * N, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return fail_cuda();
+    return OC_OK;
+}
+
+int oc_rollout(const oc_layout *lay, int64_t N, int32_t T, const uint32_t *keys, oc_state st, const oc_rollout_io *io,
+               const oc_step_extras *extras, void *stream_) {
+    if (!lay || N < 0 || T < 1 || T > 65535 || !io || !state_ok(st) || !io->obs0 || !io->obs1) return OC_ERR_INVALID_ARG;
+    if (!io->actions8 && !(io->act0 && io->act1)) return OC_ERR_INVALID_ARG;
+    if (!io->results8 && !(io->reward && io->shaped0 && io->shaped1 && io->done)) return OC_ERR_INVALID_ARG;
+    if (!keys && !(extras && extras->split_key && extras->split_num >= 1 && extras->split_first >= 0 &&
+                   extras->split_first + N <= extras->split_num && extras->split_num <= 0x7fffffffll))
+        return OC_ERR_INVALID_ARG;
+    const long long view_bytes = (long long)N * lay->host.C * OC_OBS_CHANNELS;
+    if (T > 1 && io->obs_step_stride < view_bytes) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    if (!state_aligned(st) || (keys && !aligned_to(keys, 4)) || (io->act0 && !aligned_to(io->act0, 4)) ||
+        (io->act1 && !aligned_to(io->act1, 4)) || (io->reward && !aligned_to(io->reward, 4)) ||
+        (io->shaped0 && !aligned_to(io->shaped0, 4)) || (io->shaped1 && !aligned_to(io->shaped1, 4)))
+        return OC_ERR_ALIGNMENT;
+    if (extras) {
+        const bool any = extras->episode_returns || extras->episode_lengths || extras->returned_episode_returns ||
+                         extras->returned_episode_lengths;
+        const bool all = extras->episode_returns && extras->episode_lengths && extras->returned_episode_returns &&
+                         extras->returned_episode_lengths;
+        if (any && !all) return OC_ERR_INVALID_ARG;
+    }
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.N = N; kp.T = T; kp.keys = keys; kp.st = st;
+    kp.act0 = io->act0; kp.act1 = io->act1; kp.act8 = io->actions8;
+    kp.obs0 = io->obs0; kp.obs1 = io->obs1; kp.obs_step_stride = io->obs_step_stride;
+    kp.reward = io->reward; kp.shaped0 = io->shaped0; kp.shaped1 = io->shaped1; kp.done = io->done; kp.res8 = io->results8;
+    if (extras) { kp.ex = *extras; kp.cells = extras->cells; }
+    kp.bulk_ok = aligned16(io->obs0) && aligned16(io->obs1) && (io->obs_step_stride % 16 == 0);
+    return launch_env<MODE_ROLLOUT>(lay, kp, static_cast<cudaStream_t>(stream_));
+}
+
+int oc_rollout_host(const oc_layout *lay, int64_t N, int32_t T, oc_state state, int wire, const void *h_actions,
+                    void *h_results, void *d_scratch, uint8_t *obs0, uint8_t *obs1, int64_t obs_step_stride,
+                    const oc_step_extras *extras, void *stream_) {
+    if (!lay || N < 0 || T < 1 || !h_actions || !h_results || !d_scratch || !extras || !extras->split_key)
+        return OC_ERR_INVALID_ARG;
+    if (wire != OC_WIRE_REFERENCE && wire != OC_WIRE_PACKED) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    const long long TN = (long long)T * N;
+    if (!aligned_to(d_scratch, 16) || (TN & 3)) return OC_ERR_ALIGNMENT;   // keeps every packed sub-array 4-byte aligned
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    unsigned char *d = static_cast<unsigned char *>(d_scratch);
+    oc_rollout_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.obs0 = obs0; io.obs1 = obs1; io.obs_step_stride = obs_step_stride;
+    const size_t in_bytes = (size_t)(wire == OC_WIRE_PACKED ? 1 : 8) * TN, out_bytes = (size_t)(wire == OC_WIRE_PACKED ? 1 : 13) * TN;
+    unsigned char *d_out = d + in_bytes;
+    if (wire == OC_WIRE_PACKED) {
+        io.actions8 = d; io.results8 = d_out;
+    } else {
+        io.act0 = reinterpret_cast<const int32_t *>(d); io.act1 = io.act0 + TN;
+        io.reward = reinterpret_cast<float *>(d_out); io.shaped0 = io.reward + TN; io.shaped1 = io.reward + 2 * TN;
+        io.done = reinterpret_cast<uint8_t *>(io.reward + 3 * TN);
+    }
+    if (cudaMemcpyAsync(d, h_actions, in_bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) return fail_cuda();
+    const int rc = oc_rollout(lay, N, T, nullptr, state, &io, extras, stream_);
+    if (rc != OC_OK) return rc;
+    if (cudaMemcpyAsync(h_results, d_out, out_bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return fail_cuda();
     return OC_OK;
 }
 

@@ -6,14 +6,6 @@
 
 #include <cstdint>
 
-#ifndef OC_TWO_VIEWS
-#define OC_TWO_VIEWS 0     // 1: one persistent staging image per agent view (no wait between the two bulk copies of a tile)
-#endif
-
-#ifndef OC_MIN_CTAS
-#define OC_MIN_CTAS 8       // __launch_bounds__ minimum resident CTAs per SM of the env kernel (register cap 64 at 8)
-#endif
-
 namespace {
 
 constexpr int kNumCodes = 68;        // 0..10 objects, 11..34 pot status 0..23, 35..66 agent(which,dir,inv), 67 spare
@@ -67,15 +59,18 @@ struct KParams {
     int h, w, C, WP, map_bytes, span_off, span_len, span_stride, n_pot, max_steps, random_reset, part;
     int agent_cell0, agent_cell1;
     unsigned magic_C, magic_w;
-    int n_scan, scan_bytes, nch, pf_invariant, pf_bytes;
-    int prev_bytes;          // per-warp table of the scan-cell codes currently staged (multiple of 16)
+    int n_scan, tmpl_k, tmpl_chunks, tmpl_bytes, scan_bytes, nch, pf_invariant, pf_bytes;
     unsigned magic_nch;
-    unsigned magic_ns;
-    int dbg;                 // tuning probes (OC_B200_DBG): bit 0 = do not issue the observation bulk copies
-    unsigned stagger_ns;     // OC_B200_STAGGER_NS: odd warps of a CTA start their first tile this much later
+    unsigned magic_ns, magic_tc;
+    // MODE_ROLLOUT: T steps per launch.  Per-step arrays are [T, N] (keys [T, N, 2] or ex.split_key [T, 2]); the observations
+    // of step t start obs_step_stride bytes after those of step t-1
+    int T;
+    long long obs_step_stride;
+    const uint8_t *act8;   // or NULL: packed actions u8[T, N], agent_0 | agent_1 << 4 (replaces act0 / act1)
+    uint8_t *res8;         // or NULL: packed results u8[T, N] (oc_rollout_io.results8)
 };
 
-enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBS = 2 };
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBS = 2, MODE_ROLLOUT = 3, NUM_MODES = 4 };
 
 }  // namespace
 
@@ -88,9 +83,10 @@ struct oc_layout {
     int warp_bytes;
     int warps;                 // warps per CTA: 4 unless the layout's tiles are too big for shared memory
     int pf_bytes;
+    int tmpl_smem_bytes;       // > 0: the static image (tmpl_k copies) is kept in shared memory
     unsigned char *tmpl_tile;
     int num_sms;
     int cell_stride, cell_agents;   // compact observation: bytes per env, offset of the agent entries (oc_step_extras.cells)
-    mutable int occ[6];   // resident CTAs per SM of each kernel mode (filled on first launch)
+    mutable int occ[2 * NUM_MODES];   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
 

@@ -11,7 +11,7 @@ namespace {
 // CELLS: also emit the compact form of the observations (oc_step_extras.cells); a separate instantiation so that the
 // plain kernel keeps its register budget
 template <int MODE, bool CELLS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 : 8) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevLayout *__restrict__ L = p.L;
     // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
@@ -22,6 +22,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
     unsigned short *s_pot = reinterpret_cast<unsigned short *>(s_bits + 16);
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem + kHdrFixed);   // [n_scan] span offset | cell << 16
     uint32_t *s_pf = reinterpret_cast<uint32_t *>(smem + kHdrFixed + p.scan_bytes);   // [epw*nch] prefetch plan
+    // small static images are kept in shared memory and copied by the lanes (tmpl_bytes > 0); large ones are pulled
+    // per tile from global memory by the bulk-copy engine
+    uint4 *s_tmpl = reinterpret_cast<uint4 *>(smem + kHdrFixed + p.scan_bytes + p.pf_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = p.h, w = p.w, C = p.C, WP = p.WP;
@@ -30,55 +33,43 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
     const int part = p.part;
     const int env_bytes = C * OC_OBS_CHANNELS;
     const int view_bytes = epw * env_bytes;
-    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.pf_bytes + (size_t)warp * p.warp_bytes;
-    // The warp's staging image of a tile's observations is PERSISTENT: it is filled with the layout's static image once
-    // per launch, and from then on every tile only re-writes what can differ from it -- the scan cells whose code
-    // changed against the previous tile in the same slot, the two agent cells (un-patched to the floor's all-zero
-    // record before the next tile), and the urgency plane of slots whose flag flipped.
+    unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.pf_bytes + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
     unsigned char *stage = wbase;                                              // agent_0's view of the tile
-#if OC_TWO_VIEWS
-    unsigned char *stage1 = wbase + view_bytes;                                // agent_1's view, same life cycle
-    unsigned char *smap_buf = wbase + 2 * view_bytes;                          // 2 x [epw][span_stride]
-#else
     unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
-#endif
-    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [epw] urgency flags
-    unsigned char *s_prev = reinterpret_cast<unsigned char *>(s_ap + epw);         // [epw*n_scan] staged scan codes
+    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] urgency flags
+    const uint32_t tbar = smem_u32(s_ap + 2 * epw);                                    // this warp's mbarrier (8 bytes)
     unsigned char *s_cells = wbase + p.cells_off;        // CELLS: [epw][cell_stride] staging of the compact observations
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
+    // MODE_ROLLOUT is MODE_STEP applied T times to the same tile: the state is loaded once, lives in shared memory and
+    // registers for the T steps, and is written back once (multi_agent_env.py:41-69 under the callers' lax.scan)
+    constexpr bool STEPPING = (MODE == MODE_STEP || MODE == MODE_ROLLOUT);
+    const int T = (MODE == MODE_ROLLOUT) ? p.T : 1;
+    auto load_act = [&](int ts, long long en) -> int {
+        if (MODE == MODE_ROLLOUT) {
+            const long long j = (long long)ts * p.N + en;
+            if (p.act8) { const int v = __ldg(p.act8 + j); return ai ? (v >> 4) : (v & 15); }
+            return __ldg((ai ? p.act1 : p.act0) + j);
+        }
+        return __ldg((ai ? p.act1 : p.act0) + en);
+    };
     bool bulk_pending = false;
-    // agent_1's view differs from agent_0's only in the two agent cells (overcooked.py:356-359).  With one staging
-    // image: it is sent to obs0, then -- as soon as the copy engine has READ it -- the two agent cells are re-staged
-    // from agent_1's perspective and the same buffer is sent to obs1.  With OC_TWO_VIEWS each view has its own image
-    // and both copies are issued back to back.
-    // write one cell's 26-byte record into a staged image at flat cell index g (2-byte aligned offset g*26); `urg`
-    // is channel 25 (the urgency plane, :311,:341; every record of the table has it clear)
-    auto stage_record = [&](unsigned char *img, int g, int code, uint32_t urg) {
+    // agent_1's view differs from agent_0's only in the two agent cells (overcooked.py:356-359): the staged image is
+    // sent to obs0, then -- as soon as the copy engine has READ it -- the two agent cells are re-staged from
+    // agent_1's perspective and the same buffer is sent to obs1.
+    // write one cell's 26-byte record into the staged image at flat cell index g (2-byte aligned offset g*26)
+    auto stage_record = [&](int g, int code) {
         const uint32_t *r = g_rec + code * kRecWords + ((g & 1) ? 8 : 0);
         const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(r)), v1 = __ldg(reinterpret_cast<const uint4 *>(r + 4));
-        unsigned char *dst = img + g * OC_OBS_CHANNELS;
+        unsigned char *dst = stage + g * OC_OBS_CHANNELS;
         if (g & 1) {   // offset = 2 (mod 4): shifted record -- upper half of word 0, then words 1..6
             *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(v0.x >> 16);
             uint32_t *d = reinterpret_cast<uint32_t *>(dst + 2);
-            d[0] = v0.y; d[1] = v0.z; d[2] = v0.w; d[3] = v1.x; d[4] = v1.y; d[5] = v1.z | (urg << 24);
+            d[0] = v0.y; d[1] = v0.z; d[2] = v0.w; d[3] = v1.x; d[4] = v1.y; d[5] = v1.z;
         } else {       // word aligned: words 0..5, then the lower half of word 6
             uint32_t *d = reinterpret_cast<uint32_t *>(dst);
             d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w; d[4] = v1.x; d[5] = v1.y;
-            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)((v1.z & 0xffffu) | (urg << 8));
-        }
-    };
-    // agents only ever stand on floor cells, whose record is all zero: un-patching an agent cell needs no table
-    auto stage_floor = [&](unsigned char *img, int g, uint32_t urg) {
-        unsigned char *dst = img + g * OC_OBS_CHANNELS;
-        if (g & 1) {
-            *reinterpret_cast<unsigned short *>(dst) = 0;
-            uint32_t *d = reinterpret_cast<uint32_t *>(dst + 2);
-            d[0] = 0u; d[1] = 0u; d[2] = 0u; d[3] = 0u; d[4] = 0u; d[5] = urg << 24;
-        } else {
-            uint32_t *d = reinterpret_cast<uint32_t *>(dst);
-            d[0] = 0u; d[1] = 0u; d[2] = 0u; d[3] = 0u; d[4] = 0u; d[5] = 0u;
-            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)(urg << 8);
+            *reinterpret_cast<unsigned short *>(dst + 24) = (unsigned short)(v1.z & 0xffffu);
         }
     };
 
@@ -127,9 +118,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
             f.di = p.st.agent_dir_idx[en * 2 + ai];
             f.inv = p.st.agent_inv[en * 2 + ai];
             f.t = p.st.time[en];
-            if (MODE == MODE_STEP) {
+            if (STEPPING) {
                 f.dir = reinterpret_cast<const unsigned short *>(p.st.agent_dir)[en * 2 + ai];
-                f.act = __ldg((ai ? p.act1 : p.act0) + en);
+                f.act = load_act(0, en);
             }
         }
         return f;
@@ -139,16 +130,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
     // wait for the previous kernel's memory to be visible before touching any environment state.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     {
-        {   // static image of a whole tile (L2-resident, 16-byte aligned) -> this warp's staging image(s)
-            const uint4 *tsrc = reinterpret_cast<const uint4 *>(p.tmpl_tile);
-            for (int f = lane; f < (view_bytes >> 4); f += 32) {
-                const uint4 v = __ldg(tsrc + f);
-                reinterpret_cast<uint4 *>(stage)[f] = v;
-#if OC_TWO_VIEWS
-                reinterpret_cast<uint4 *>(stage1)[f] = v;
-#endif
-            }
-            for (int i = lane; i < (p.prev_bytes >> 2); i += 32) reinterpret_cast<uint32_t *>(s_prev)[i] = 0xffffffffu;
+        if (p.tmpl_bytes) {
+            const uint4 *tsrc = reinterpret_cast<const uint4 *>(L->obs_tmpl);
+            for (int i = tid; i < p.tmpl_chunks; i += cta_threads) s_tmpl[i] = __ldg(tsrc + i);
         }
         for (int i = tid; i < p.n_scan; i += cta_threads) s_scan[i] = L->scan[i];
         if (p.pf_invariant) {
@@ -166,6 +150,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
         if (tid < 8) { s_bits[tid] = L->wall_bits[tid]; s_bits[8 + tid] = L->blocked_bits[tid]; }
         if (tid < OC_MAX_SPECIAL) s_pot[tid] = L->pot_cell[tid];
     }
+    // The static observation image of a tile lives in global memory (L2-resident, tile-sized); each tile's staging
+    // buffer is (re)filled from it by ONE bulk asynchronous copy that completes on this warp's mbarrier while the
+    // step logic runs.
+    uint32_t tphase = 0;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (CELLS)         // padding bytes of the compact form stay 0xFF
         for (int i = lane; i < (epw * p.cell_stride) >> 2; i += 32) reinterpret_cast<uint32_t *>(s_cells)[i] = 0xffffffffu;
     __syncthreads();   // the tables (incl. the prefetch plan) are complete before any warp uses them
@@ -173,13 +165,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
     long long tile = (long long)blockIdx.x * cta_warps + warp;
     int buf = 0;
     Fields nf;
-    int prev_cell = -1, surg = 0;   // what this lane left in the staging image: its agent cell, its slot's urgency flag
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
-    if (p.stagger_ns && (warp & 1)) {   // tuning probe: de-phase the two halves of the CTA's warps
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do { __nanosleep(200); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < p.stagger_ns);
-    }
 
     for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
         const long long env0 = tile * epw;
@@ -194,6 +180,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
         unsigned char *my_span = smap + es * span_stride + ((m0 + es * p.map_bytes) & 15);
         unsigned char *g_span = g_tile + es * p.map_bytes;                                   // same bytes in HBM
 
+        // ------------------------------------------------ (0) refill the staging buffer with the static image
+        auto refill_stage = [&]() {
+            if (!p.tmpl_bytes) {
+                if (lane == 0) {
+                    if (bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // obs1 of the previous tile / step
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tbar), "r"(view_bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"(smem_u32(stage)), "l"(p.tmpl_tile), "r"(view_bytes), "r"(tbar) : "memory");
+                }
+                bulk_pending = false;
+            }
+        };
+        refill_stage();
         // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
         const Fields cf = nf;
         if (tile + tile_stride < p.n_tiles) {
@@ -203,21 +202,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        const int px = (int)cf.pos.x, py = (int)cf.pos.y, di = cf.di, inv = cf.inv, t = cf.t;
-        const int dx = (int)(signed char)(cf.dir & 0xffu), dy = (int)(signed char)(cf.dir >> 8);
-        const int act = clampi(cf.act, 0, 5);
+        int px = (int)cf.pos.x, py = (int)cf.pos.y, di = cf.di, inv = cf.inv, t = cf.t;
+        int dx = (int)(signed char)(cf.dir & 0xffu), dy = (int)(signed char)(cf.dir >> 8);
+        int act = clampi(cf.act, 0, 5);
+        float lw_er = 0.f, lw_el = 0.f, lw_rr = 0.f, lw_rl = 0.f;   // LogWrapper trackers of this agent
+        int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // MODE_ROLLOUT: statistics of the T steps
         __syncwarp();
 
+      for (int ts = 0; ts < T; ++ts) {
+        const bool last_ts = (MODE != MODE_ROLLOUT) || ts == T - 1;
+        if (MODE == MODE_ROLLOUT && ts > 0) refill_stage();   // every step emits from a fresh static image
+        int nact = 4;
+        if (MODE == MODE_ROLLOUT && !last_ts && active) nact = load_act(ts + 1, env);   // consumed a whole step later
         int nx = px, ny = py, ndi = di, ninv = inv, t_out = t, term_out = 0;
         bool done = (MODE == MODE_RESET);
         int rew = 0, shaped = 0;
         // a cell is updated in the staged span AND, in place, in HBM (only cells that change are ever written back)
+        // (MODE_ROLLOUT: the staged span alone; every span is stored once, after the last step)
         auto put_cell = [&](int off, int a, int b, int c) {
             my_span[off] = (unsigned char)a; my_span[off + 1] = (unsigned char)b; my_span[off + 2] = (unsigned char)c;
-            g_span[off] = (unsigned char)a; g_span[off + 1] = (unsigned char)b; g_span[off + 2] = (unsigned char)c;
+            if (MODE != MODE_ROLLOUT) {
+                g_span[off] = (unsigned char)a; g_span[off + 1] = (unsigned char)b; g_span[off + 2] = (unsigned char)c;
+            }
         };
 
-        if (MODE == MODE_STEP) {
+        if (STEPPING) {
             // ------------------------------------------------------------ movement (overcooked.py:370-431)
             const bool is_move = act < 4;
             const int cx = clampi(px + (is_move ? dir_x(act) : dx), 0, w - 1);
@@ -264,7 +273,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                     const int pyy = (int)fastdiv((unsigned)pc, p.magic_w), pxx = pc - pyy * w;
                     const int off = (pyy * WP + pxx) * 3 + 2;
                     const int s = my_span[off];
-                    if (s >= 1 && s <= 20) { my_span[off] = (unsigned char)(s - 1); g_span[off] = (unsigned char)(s - 1); }
+                    if (s >= 1 && s <= 20) {
+                        my_span[off] = (unsigned char)(s - 1);
+                        if (MODE != MODE_ROLLOUT) g_span[off] = (unsigned char)(s - 1);
+                    }
                 }
             }
             rew += __shfl_xor_sync(0xffffffffu, rew, 1);                   // :502 reward = alice + bob
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
         }
 
         // -------------------------------------------------------------------- (3) reset (overcooked.py:136-248)
-        bool full_writeback = (MODE == MODE_RESET);
+        bool full_writeback = (MODE == MODE_RESET) || (MODE == MODE_ROLLOUT);
         if (MODE != MODE_OBS) {
             const unsigned done_mask = __ballot_sync(0xffffffffu, done && active);
             if (done_mask) {
@@ -306,13 +318,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                     __syncwarp();
                     if (done && active) {
                         uint32_t k0, k1;
-                        if (p.keys) { k0 = __ldg(p.keys + env * 2); k1 = __ldg(p.keys + env * 2 + 1); }
+                        // MODE_ROLLOUT: step ts has its own keys -- row ts of keys[T, N, 2] or of split_key[T, 2]
+                        const long long kj = (MODE == MODE_ROLLOUT) ? (long long)ts * p.N + env : env;
+                        if (p.keys) { k0 = __ldg(p.keys + kj * 2); k1 = __ldg(p.keys + kj * 2 + 1); }
                         else {   // the caller's split(key, num_envs) fused in: derive this env's row on demand
-                            split_row(part, __ldg(p.ex.split_key), __ldg(p.ex.split_key + 1), p.ex.split_num,
-                                      p.ex.split_first + env, k0, k1);
+                            const uint32_t *sk = p.ex.split_key + ((MODE == MODE_ROLLOUT) ? 2 * ts : 0);
+                            split_row(part, __ldg(sk), __ldg(sk + 1), p.ex.split_num, p.ex.split_first + env, k0, k1);
                         }
                         uint32_t s0, s1;
-                        if (MODE == MODE_STEP) { split2(part, k0, k1, s0, s1); k0 = s0; k1 = s1; }   // key_reset
+                        if (STEPPING) { split2(part, k0, k1, s0, s1); k0 = s0; k1 = s1; }   // key_reset
                         uint32_t a0, a1, d0, d1, q0, q1, i0, i1;
                         split2(part, k0, k1, a0, a1);      // :164 agent cells
                         split2(part, k0, k1, d0, d1);      // :173 directions
@@ -366,8 +380,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
         }
 
         // LogWrapper trackers of this agent: requested here so the loads overlap the observation phase
-        float lw_er = 0.f, lw_el = 0.f, lw_rr = 0.f, lw_rl = 0.f;
-        if (MODE == MODE_STEP && p.ex.episode_returns && active) {
+        if ((MODE == MODE_STEP || (MODE == MODE_ROLLOUT && ts == 0)) && p.ex.episode_returns && active) {
             const long long j = env * 2 + ai;
             lw_er = p.ex.episode_returns[j]; lw_el = p.ex.episode_lengths[j];
             lw_rr = p.ex.returned_episode_returns[j]; lw_rl = p.ex.returned_episode_lengths[j];
@@ -375,43 +388,38 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
 
         // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
         bool obs1_pending = false;
-        int code_v1 = 0, my_cell = 0;
-        const size_t obs_off = (size_t)env0 * env_bytes;
-        const uint32_t urg = (uint32_t)((p.max_steps - t_out) < 40);                          // :311
+        int code_v1 = 0, my_cell = 0, urg_lane = 0;
+        const size_t obs_off = (size_t)env0 * env_bytes + ((MODE == MODE_ROLLOUT) ? (size_t)ts * (size_t)p.obs_step_stride : 0);
         {
-            if (active && ai == 0) s_ap[e] = urg;
-            if (bulk_pending) {   // the previous tile's copies must have finished READING the staging image(s)
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                bulk_pending = false;
+            const int urg = (p.max_steps - t_out) < 40;                                       // :311
+            if (active) s_ap[lane] = (uint32_t)urg;
+            // (4a) base image
+            if (p.tmpl_bytes) {   // copied by the lanes from shared memory, 16 bytes per lane-step
+                if (bulk_pending) {   // the previous tile's obs1 copy must have finished READING the staging buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    bulk_pending = false;
+                    __syncwarp();
+                }
+                const int n_chunks = (n_valid * env_bytes + 15) >> 4;
+                uint4 *dst = reinterpret_cast<uint4 *>(stage);
+                int src = lane;                                                         // tiles start on a template period
+                src -= (int)fastdiv((unsigned)src, p.magic_tc) * p.tmpl_chunks;
+                const int step = 32 - (int)fastdiv(32u, p.magic_tc) * p.tmpl_chunks;      // 32 mod tmpl_chunks
+                for (int f = lane; f < n_chunks; f += 32) {
+                    dst[f] = s_tmpl[src];
+                    src += step;
+                    if (src >= p.tmpl_chunks) src -= p.tmpl_chunks;
+                }
+            } else {              // wait for the bulk copy issued at the top of the tile
+                uint32_t ok = 0;
+                while (!ok) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(tbar), "r"(tphase) : "memory");
+                }
+                tphase ^= 1u;
             }
             __syncwarp();
-            // (4a) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left -- only slots whose
-            // flag differs from what the image holds are touched
-            {
-                const unsigned chg = __ballot_sync(0xffffffffu, active && ai == 0 && (int)urg != surg);
-                if (chg) {
-                    const int n_cells = n_valid * C;
-                    for (int g = lane; g < n_cells; g += 32) {
-                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
-                        if ((chg >> (2 * el)) & 1u) {
-                            stage[g * OC_OBS_CHANNELS + 25] = (unsigned char)s_ap[el];
-#if OC_TWO_VIEWS
-                            stage1[g * OC_OBS_CHANNELS + 25] = (unsigned char)s_ap[el];
-#endif
-                        }
-                    }
-                }
-                if (active) surg = (int)urg;
-            }
-            // (4b) the cell this lane's agent occupied in the previous tile of this slot goes back to the floor record
-            if (active && prev_cell >= 0) {
-                stage_floor(stage, prev_cell, urg);
-#if OC_TWO_VIEWS
-                stage_floor(stage1, prev_cell, urg);
-#endif
-            }
-            // (4c) cells that can deviate from the static image: counters next to a walkable cell (loose items) and pots;
-            // re-staged only where the code differs from what the previous tile left in this slot
+            // (4b) cells that can deviate from the base image: counters next to a walkable cell (loose items) and pots
             {
                 const int total = n_valid * p.n_scan;
                 for (int f = lane; f < total; f += 32) {
@@ -419,31 +427,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                     const uint32_t sc = s_scan[f - el * p.n_scan];
                     const unsigned char *c = smap + el * span_stride + ((m0 + el * p.map_bytes) & 15) + (int)(sc & 0xffffu);
                     const int o = c[0], st = c[2];
-                    const int code = (o == 8) ? kCodePot + min(st, 23) : min(o, 10);
-                    if (s_prev[f] != code) {
-                        s_prev[f] = (unsigned char)code;
-                        stage_record(stage, el * C + (int)(sc >> 16), code, s_ap[el]);
-#if OC_TWO_VIEWS
-                        stage_record(stage1, el * C + (int)(sc >> 16), code, s_ap[el]);
-#endif
-                    }
+                    if (o == 8 ? (st != 23) : (o != 2 && o != 10))
+                        stage_record(el * C + (int)(sc >> 16), (o == 8) ? kCodePot + min(st, 23) : min(o, 10));
                     if (CELLS)     // the compact form of this observation (include/oc_b200.h, oc_step_extras.cells)
                         s_cells[el * p.cell_stride + (f - el * p.n_scan)] =
-                            (uint8_t)((o == 8 ? (st != 23) : (o != 2 && o != 10)) ? code : 0xff);
+                            (uint8_t)((o == 8 ? (st != 23) : (o != 2 && o != 10)) ? ((o == 8) ? kCodePot + min(st, 23) : min(o, 10)) : 0xff);
                 }
             }
             __syncwarp();
-            // (4d) agent cells show the agent, its direction and what it holds (:313-323, :345-353); agent_1 sees the
-            // same cell with "which" flipped (it is the viewer)
-            my_cell = es * C + ny * w + nx;
-            code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
-            if (active) {
-                stage_record(stage, my_cell, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)), urg);
-#if OC_TWO_VIEWS
-                stage_record(stage1, my_cell, code_v1, urg);
-#endif
-                prev_cell = my_cell;
-            }
+            // (4c) agent cells show the agent, its direction and what it holds (:313-323, :345-353)
+            if (active) stage_record(es * C + ny * w + nx, kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2)));
             if (CELLS) {
                 if (active) {
                     unsigned char *cl = s_cells + es * p.cell_stride + p.cell_agents;
@@ -454,26 +447,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                 __syncwarp();
                 // the tile's compact observations are contiguous in global memory: 16-byte stores
                 const uint4 *src = reinterpret_cast<const uint4 *>(s_cells);
-                uint4 *dst = reinterpret_cast<uint4 *>(p.cells + env0 * p.cell_stride);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.cells + (env0 + ((MODE == MODE_ROLLOUT) ? (long long)ts * p.N : 0)) * p.cell_stride);
                 for (int i = lane; i < (n_valid * p.cell_stride) >> 4; i += 32) dst[i] = src[i];
             }
+            __syncwarp();
+            // (4d) urgency plane (:311, :341): channel 25 of every cell of an env with < 40 steps left
+            {
+                const unsigned urg_mask = __ballot_sync(0xffffffffu, active && urg && ai == 0);
+                if (urg_mask) {
+                    const int n_cells = n_valid * C;
+                    for (int g = lane; g < n_cells; g += 32) {
+                        const int el = (int)fastdiv((unsigned)g, p.magic_C);
+                        if (s_ap[2 * el]) stage[g * OC_OBS_CHANNELS + 25] = 1;
+                    }
+                }
+            }
+            // this lane's agent cell as agent_1 sees it: "which" flipped (agent_1 is the viewer)
+            code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
+            my_cell = es * C + ny * w + nx;
+            urg_lane = urg;
             if (p.bulk_ok && n_valid == epw) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0 && !(p.dbg & 1)) {
+                if (lane == 0) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
-#if OC_TWO_VIEWS
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage1)), "r"(view_bytes) : "memory");
-#endif
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-#if OC_TWO_VIEWS
-                bulk_pending = true;
-#else
                 obs1_pending = true;      // issued after the state write-back below, which hides the engine's read
-#endif
             } else {
                 // ragged last tile (or unaligned caller buffers): plain stores, 2-byte granular
                 __syncwarp();
@@ -482,22 +483,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                 unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + obs_off);
                 unsigned short *g1 = reinterpret_cast<unsigned short *>(p.obs1 + obs_off);
                 for (int k = lane; k < (nb >> 1); k += 32) g0[k] = h0[k];
-#if OC_TWO_VIEWS
-                const unsigned short *h1 = reinterpret_cast<const unsigned short *>(stage1);
-                for (int k = lane; k < (nb >> 1); k += 32) g1[k] = h1[k];
-#else
                 __syncwarp();
-                if (active) stage_record(stage, my_cell, code_v1, urg);
+                if (active) stage_record(my_cell, code_v1);
+                if (urg && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
                 __syncwarp();
                 for (int k = lane; k < (nb >> 1); k += 32) g1[k] = h0[k];
-#endif
             }
         }
 
         // ---------------------------------------------------------------- (5) write the state back, in place
         if (MODE != MODE_OBS) {
             __syncwarp();
-            if (full_writeback) {   // a reset rewrote whole interiors: store the staged spans (rare: 1 step in max_steps)
+            if (full_writeback && last_ts) {   // whole interiors: after a reset (rare: 1 step in max_steps) / after a rollout's last step
                 for (int el = 0; el < n_valid; ++el) {
                     const int mis = (m0 + el * p.map_bytes) & 15;
                     const unsigned char *src = smap + el * span_stride;          // slot and HBM agree modulo 16
@@ -506,7 +503,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                         *reinterpret_cast<uint32_t *>(dstg + o) = *reinterpret_cast<const uint32_t *>(src + o);
                 }
             }
-            if (active) {
+            if (active && last_ts) {
                 reinterpret_cast<uint2 *>(p.st.agent_pos)[env * 2 + ai] = make_uint2((uint32_t)nx, (uint32_t)ny);
                 reinterpret_cast<char2 *>(p.st.agent_dir)[env * 2 + ai] = make_char2((signed char)dir_x(ndi), (signed char)dir_y(ndi));
                 p.st.agent_dir_idx[env * 2 + ai] = ndi;
@@ -516,11 +513,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                     p.st.terminal[env] = (uint8_t)term_out;   // stepped: done is False; reset: False (overcooked.py:242)
                 }
             }
-            if (MODE == MODE_STEP) {
+            if (STEPPING) {
                 int st_rr = 0, st_rl = 0;
+                const long long oi = env + ((MODE == MODE_ROLLOUT) ? (long long)ts * p.N : 0);   // row of the per-step outputs
+                if (MODE == MODE_ROLLOUT && p.res8) {
+                    // packed results (oc_rollout_io.results8): reward / 20 | shaped0 class << 2 | shaped1 class << 4 | done << 6
+                    const int sc = shaped == 0 ? 0 : (shaped == 3 ? 1 : 2);
+                    const int osc = __shfl_xor_sync(0xffffffffu, sc, 1);
+                    if (active && ai == 0) p.res8[oi] = (uint8_t)((rew / 20) | (sc << 2) | (osc << 4) | ((int)done << 6));
+                } else if (active) {
+                    if (ai == 0) { p.reward[oi] = (float)rew; p.done[oi] = (uint8_t)done; }
+                    (ai ? p.shaped1 : p.shaped0)[oi] = (float)shaped;
+                }
                 if (active) {
-                    if (ai == 0) { p.reward[env] = (float)rew; p.done[env] = (uint8_t)done; }
-                    (ai ? p.shaped1 : p.shaped0)[env] = (float)shaped;
                     if (p.ex.episode_returns) {   // wrappers/baselines.py:90-106, this lane = agent ai
                         const long long j = env * 2 + ai;
                         // pin the four loaded trackers here: without this the compiler hoists their first use right
@@ -529,16 +534,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                         const float keep = done ? 0.f : 1.f, dn = done ? 1.f : 0.f;
                         const float nr = lw_er + (float)rew;
                         const float nl = lw_el + 1.f;
-                        p.ex.episode_returns[j] = nr * keep;
-                        p.ex.episode_lengths[j] = nl * keep;
                         const float rr = lw_rr * keep + nr * dn;
                         const float rl = lw_rl * keep + nl * dn;
-                        p.ex.returned_episode_returns[j] = rr;
-                        p.ex.returned_episode_lengths[j] = rl;
-                        if (p.ex.returned_episode) p.ex.returned_episode[j] = (uint8_t)done;
+                        lw_er = nr * keep; lw_el = nl * keep; lw_rr = rr; lw_rl = rl;   // MODE_ROLLOUT: carried to the next step
+                        if (last_ts) {
+                            p.ex.episode_returns[j] = lw_er;
+                            p.ex.episode_lengths[j] = lw_el;
+                            p.ex.returned_episode_returns[j] = rr;
+                            p.ex.returned_episode_lengths[j] = rl;
+                        }
+                        if (p.ex.returned_episode) p.ex.returned_episode[oi * 2 + ai] = (uint8_t)done;
                         if (ai == 0 && done) { st_rr = (int)rr; st_rl = (int)rl; }
                     } else if (p.ex.returned_episode) {
-                        p.ex.returned_episode[env * 2 + ai] = (uint8_t)done;
+                        p.ex.returned_episode[oi * 2 + ai] = (uint8_t)done;
                     }
                 }
                 if (p.ex.stats) {   // exact integer sums: warp-reduced per tile, one atomic per non-zero counter
@@ -546,23 +554,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
                     int v_rew = (active && ai == 0) ? rew : 0;
                     int v_s0 = (active && ai == 0) ? shaped : 0;
                     int v_s1 = (active && ai == 1) ? shaped : 0;
-                    #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        v_done += __shfl_xor_sync(0xffffffffu, v_done, o);
-                        v_rew += __shfl_xor_sync(0xffffffffu, v_rew, o);
-                        v_s0 += __shfl_xor_sync(0xffffffffu, v_s0, o);
-                        v_s1 += __shfl_xor_sync(0xffffffffu, v_s1, o);
-                        st_rr += __shfl_xor_sync(0xffffffffu, st_rr, o);
-                        st_rl += __shfl_xor_sync(0xffffffffu, st_rl, o);
+                    if (MODE == MODE_ROLLOUT) {   // summed per lane over the T steps, reduced once per tile
+                        acc_done += v_done; acc_rew += v_rew; acc_s0 += v_s0; acc_s1 += v_s1; acc_rr += st_rr; acc_rl += st_rl;
+                        v_done = acc_done; v_rew = acc_rew; v_s0 = acc_s0; v_s1 = acc_s1; st_rr = acc_rr; st_rl = acc_rl;
                     }
-                    if (lane == 0) {
-                        unsigned long long *sp = reinterpret_cast<unsigned long long *>(p.ex.stats);
-                        if (v_done) atomicAdd(sp + 0, (unsigned long long)v_done);
-                        if (v_rew) atomicAdd(sp + 1, (unsigned long long)v_rew);
-                        if (v_s0) atomicAdd(sp + 2, (unsigned long long)v_s0);
-                        if (v_s1) atomicAdd(sp + 3, (unsigned long long)v_s1);
-                        if (st_rr) atomicAdd(sp + 4, (unsigned long long)st_rr);
-                        if (st_rl) atomicAdd(sp + 5, (unsigned long long)st_rl);
+                    if (last_ts) {
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            v_done += __shfl_xor_sync(0xffffffffu, v_done, o);
+                            v_rew += __shfl_xor_sync(0xffffffffu, v_rew, o);
+                            v_s0 += __shfl_xor_sync(0xffffffffu, v_s0, o);
+                            v_s1 += __shfl_xor_sync(0xffffffffu, v_s1, o);
+                            st_rr += __shfl_xor_sync(0xffffffffu, st_rr, o);
+                            st_rl += __shfl_xor_sync(0xffffffffu, st_rl, o);
+                        }
+                        if (lane == 0) {
+                            unsigned long long *sp = reinterpret_cast<unsigned long long *>(p.ex.stats);
+                            if (v_done) atomicAdd(sp + 0, (unsigned long long)v_done);
+                            if (v_rew) atomicAdd(sp + 1, (unsigned long long)v_rew);
+                            if (v_s0) atomicAdd(sp + 2, (unsigned long long)v_s0);
+                            if (v_s1) atomicAdd(sp + 3, (unsigned long long)v_s1);
+                            if (st_rr) atomicAdd(sp + 4, (unsigned long long)st_rr);
+                            if (st_rl) atomicAdd(sp + 5, (unsigned long long)st_rl);
+                        }
                     }
                 }
             }
@@ -570,10 +584,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
         if (obs1_pending) {   // agent_1's view: re-stage the two agent cells once the engine has read the image
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
-            if (active) stage_record(stage, my_cell, code_v1, urg);
+            if (active) stage_record(my_cell, code_v1);
+            if (urg_lane && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0 && !(p.dbg & 1)) {
+            if (lane == 0) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -581,9 +596,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OC_MIN_CTAS) oc_env_kernel(
             bulk_pending = true;
         }
         __syncwarp();
+        if (MODE == MODE_ROLLOUT) {   // the next step starts from what this one produced (agent_dir is DIR_TO_VEC[dir_idx], :434-435)
+            px = nx; py = ny; di = ndi; inv = ninv; t = t_out;
+            dx = dir_x(ndi); dy = dir_y(ndi);
+            act = clampi(nact, 0, 5);
+        }
+      }   // ts
     }
-    if (MODE == MODE_STEP && p.ex.stats && blockIdx.x == 0 && tid == 0)   // every env stepped once
-        atomicAdd(reinterpret_cast<unsigned long long *>(p.ex.stats) + 6, (unsigned long long)p.N);
+    if (STEPPING && p.ex.stats && blockIdx.x == 0 && tid == 0)   // every env stepped T times
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.ex.stats) + 6, (unsigned long long)p.N * (unsigned long long)T);
     if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 

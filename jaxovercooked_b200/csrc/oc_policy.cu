@@ -54,8 +54,11 @@ struct oc_policy {
     PolicySmall *small;
     uint8_t *tmpl;
     int pl;
-    // compact-observation source (desc->layout given)
-    const oc_layout *layout;
+    // compact-observation source (desc->layout given): everything the policy needs from the layout is COPIED at creation
+    // (record table, cell geometry), so the policy does not depend on the layout's lifetime
+    bool has_cells;
+    int C, cell_stride, cell_agents, n_scan, device;
+    unsigned *rec;              // [OC_NUM_CELL_CODES][kRecWords]: the observation record of every cell code
     __half *emb;
     uint8_t *scan_cells;
     mutable bool repacked;      // set by create / update, cleared by the next forward
@@ -92,15 +95,15 @@ static int policy_pack(oc_policy *p, const oc_policy_desc *d, cudaStream_t strea
     a.tmpl = p->tmpl; a.w1 = p->w1; a.w2img = p->w2img; a.small = p->small; a.K = p->K; a.A = p->A;
     p->repacked = true;
     oc_policy_pack_kernel<<<p->num_sms * 2, 256, 0, stream>>>(a);
-    if (p->layout)
-        oc_policy_embed_kernel<<<p->layout->host.C * OC_NUM_CELL_CODES + 2, kHid2, 0, stream>>>(
-            d->kernel[0], d->kernel[3], p->tmpl, p->layout->dev, p->layout->host.C, p->emb);
+    if (p->has_cells)
+        oc_policy_embed_kernel<<<p->C * OC_NUM_CELL_CODES + 2, kHid2, 0, stream>>>(
+            d->kernel[0], d->kernel[3], p->tmpl, p->rec, p->C, p->emb);
     return cudaGetLastError() == cudaSuccess ? OC_OK : OC_ERR_CUDA;
 }
 
 void oc_policy_destroy(oc_policy *p) {
     if (!p) return;
-    cudaFree(p->w1); cudaFree(p->w2img); cudaFree(p->small); cudaFree(p->tmpl); cudaFree(p->emb); cudaFree(p->scan_cells);
+    cudaFree(p->w1); cudaFree(p->w2img); cudaFree(p->small); cudaFree(p->tmpl); cudaFree(p->emb); cudaFree(p->scan_cells); cudaFree(p->rec);
     delete p;
 }
 
@@ -119,6 +122,7 @@ int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
     if (!p) return OC_ERR_INVALID_ARG;
     p->K = d->obs_dim; p->A = d->action_dim; p->act = d->activation; p->part = d->prng_mode;
     p->num_sms = prop.multiProcessorCount;
+    p->device = dev;
     const int g = gcd16(p->K);
     p->gshift = g == 16 ? 4 : g == 8 ? 3 : g == 4 ? 2 : g == 2 ? 1 : 0;
     p->nvar = 16 / g;
@@ -137,18 +141,21 @@ int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
     const uint8_t *tmpl_src = d->obs_template;
     if (d->layout) {      // the env's own static image, and the (view, cell, code) embedding table for oc_policy_forward_cells
         const oc_layout *lay = d->layout;
-        if (lay->host.C * OC_OBS_CHANNELS != p->K) { oc_policy_destroy(p); return OC_ERR_INVALID_ARG; }
+        if (lay->host.C * OC_OBS_CHANNELS != p->K || lay->device != dev) { oc_policy_destroy(p); return OC_ERR_INVALID_ARG; }
         tmpl_src = lay->host.obs_tmpl;
         if (lay->cell_stride <= 64) {
             uint8_t sc[64] = {0};
             for (int i = 0; i < lay->host.n_scan; ++i) sc[i] = (uint8_t)(lay->host.scan[i] >> 16);
             if (cudaMalloc(&p->emb, ((size_t)lay->host.C * OC_NUM_CELL_CODES + 2) * kHid2 * sizeof(__half)) != cudaSuccess ||
                 cudaMalloc(&p->scan_cells, 64) != cudaSuccess ||
-                cudaMemcpy(p->scan_cells, sc, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaMemcpy(p->scan_cells, sc, 64, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMalloc(&p->rec, sizeof(lay->host.rec)) != cudaSuccess ||
+                cudaMemcpy(p->rec, lay->host.rec, sizeof(lay->host.rec), cudaMemcpyHostToDevice) != cudaSuccess) {
                 oc_policy_destroy(p);
                 return OC_ERR_CUDA;
             }
-            p->layout = lay;
+            p->has_cells = true;
+            p->C = lay->host.C; p->cell_stride = lay->cell_stride; p->cell_agents = lay->cell_agents; p->n_scan = lay->host.n_scan;
             if (cudaFuncSetAttribute(pick_kernel(p->act, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cells) != cudaSuccess) {
                 oc_policy_destroy(p);
                 return OC_ERR_CUDA;
@@ -203,11 +210,11 @@ int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *
 int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells, float *logits, float *value,
                              const uint32_t *key, int32_t *action, float *log_prob, void *stream_) {
     if (!p || N < 0 || !cells) return OC_ERR_INVALID_ARG;
-    if (!p->layout) return OC_ERR_UNSUPPORTED_LAYOUT;      // created without a layout, or its compact form is too wide
+    if (!p->has_cells) return OC_ERR_UNSUPPORTED_LAYOUT;      // created without a layout, or its compact form is too wide
     if ((action || log_prob) && !key) return OC_ERR_INVALID_ARG;
     if (N == 0) return OC_OK;
     const int64_t M = 2 * N;
-    if (M * p->A > 0x7fffffffll || M * p->layout->cell_stride > 0x7fffffffll) return OC_ERR_INVALID_ARG;
+    if (M * p->A > 0x7fffffffll || M * p->cell_stride > 0x7fffffffll) return OC_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(key) |
          reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(log_prob)) & 3u)
         return OC_ERR_ALIGNMENT;
@@ -220,8 +227,8 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     k.n_tiles = (int)((N + k.rpt / 2 - 1) / (k.rpt / 2));
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     k.cells = cells; k.emb = p->emb; k.scan_cells = p->scan_cells;
-    k.cell_stride = p->layout->cell_stride; k.cell_agents = p->layout->cell_agents; k.n_scan = p->layout->host.n_scan;
-    k.C = p->layout->host.C;
+    k.cell_stride = p->cell_stride; k.cell_agents = p->cell_agents; k.n_scan = p->n_scan;
+    k.C = p->C;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
     return launch_policy(p, pick_kernel(p->act, 0), grid, kCellWarps * 32, p->smem_cells, k, static_cast<cudaStream_t>(stream_));
 }

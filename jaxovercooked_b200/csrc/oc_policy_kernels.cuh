@@ -785,7 +785,7 @@ __global__ void oc_policy_pack_kernel(const PackArgs a) {
 // with the viewer bit of its code flipped).  One CTA per table row, one thread per hidden unit.
 // Rows C*68 and C*68 + 1: zeros (padding entry) and the urgency plane (channel 25 of every cell).
 __global__ void oc_policy_embed_kernel(const float *__restrict__ k_actor, const float *__restrict__ k_critic,
-                                       const uint8_t *__restrict__ tmpl, const DevLayout *__restrict__ L, int C, __half *emb) {
+                                       const uint8_t *__restrict__ tmpl, const unsigned *__restrict__ rec, int C, __half *emb) {
     const int row = blockIdx.x, j = threadIdx.x;
     const float *kern = j < kHid ? k_actor : k_critic;
     const int jj = j < kHid ? j : j - kHid;
@@ -794,7 +794,7 @@ __global__ void oc_policy_embed_kernel(const float *__restrict__ k_actor, const 
     if (row < n_rows) {
         const int cell = row / OC_NUM_CELL_CODES, code = row % OC_NUM_CELL_CODES;
         for (int ch = 0; ch < OC_OBS_CHANNELS; ++ch) {
-            const int rv = (int)((L->rec[code][ch >> 2] >> (8 * (ch & 3))) & 255u);
+            const int rv = (int)((rec[code * kRecWords + (ch >> 2)] >> (8 * (ch & 3))) & 255u);
             const int d = rv - (int)tmpl[cell * OC_OBS_CHANNELS + ch];
             if (d) s = fmaf((float)d, kern[(size_t)(cell * OC_OBS_CHANNELS + ch) * kHid + jj], s);
         }

@@ -306,6 +306,114 @@ class Overcooked:
         infos = {"shaped_reward": {"agent_0": sh0, "agent_1": sh1}}            # :125, :133
         return obs, new_state, rewards, dones, infos
 
+    def rollout(self, keys, state, actions, *, out=None, log=None, stats=None):
+        """T consecutive `env.step` calls on the same batch in ONE launch (`oc_rollout`): the callers'
+        `jax.lax.scan(_env_step, ..., length=T)` over `jax.vmap(env.step)` with the actions given
+        (baselines/unused/random_actions.py:197-225).  `state` is stepped IN PLACE (a donated scan carry).
+
+          keys     uint32[T, N, 2] per-step per-env keys, or uint32[T, 2]: step t uses split(keys[t], N) derived in the kernel
+                   (or a (keys[T, 2], num, first) tuple for one shard of a global batch of `num` envs)
+          actions  {"agent_0": int32[T, N], "agent_1": int32[T, N]}, or a uint8[T, N] tensor (agent_0 | agent_1 << 4)
+          out      optional preallocated results: "obs" uint8[T, 2, N, h, w, 26] (the learners' layout: out["obs"][t].view(2N, -1)
+                   is batchify(obs) of step t) or "obs0"/"obs1" uint8[T, N, h, w, 26]; "reward"/"shaped0"/"shaped1" float32[T, N],
+                   "done" bool[T, N]; or "results8" uint8[T, N] (packed) instead of the four; "cells" uint8[T, N, cell_stride]
+          log      LogWrapper trackers [N, 2] (updated T times, in place); log["returned_episode"], if given, is [T, N, 2]
+        Returns (obs, state, rewards, dones, infos) with a leading T on every array."""
+        dev, h, w = self.device, self.height, self.width
+        e = _lib.StepExtras()
+        key_ptr = None
+        split = None
+        if isinstance(keys, tuple):
+            keys, num, first = keys
+            split = (int(num), int(first))
+        if not torch.is_tensor(keys) or keys.dtype != torch.uint32 or keys.device != dev or not keys.is_contiguous():
+            raise ValueError("keys must be a contiguous uint32 tensor on the env's device")
+        if keys.dim() == 3:
+            T, n = int(keys.shape[0]), int(keys.shape[1])
+            if keys.shape[2] != 2 or split is not None:
+                raise ValueError("keys must be uint32[T, N, 2] or uint32[T, 2]")
+            key_ptr = keys.data_ptr()
+        elif keys.dim() == 2 and keys.shape[1] == 2:
+            T = int(keys.shape[0])
+            n = int(state.time.shape[0])
+            e.split_key = keys.data_ptr()
+            e.split_num, e.split_first = split if split is not None else (n, 0)
+        else:
+            raise ValueError("keys must be uint32[T, N, 2] or uint32[T, 2]")
+        batch = (n,)
+        sp = self._state_ptrs(state, batch)
+        io = _lib.RolloutIO()
+        if torch.is_tensor(actions):
+            self._check(actions, "actions", torch.uint8, (T, n))
+            io.actions8 = actions.data_ptr()
+        else:
+            a0 = self._check(actions["agent_0"], "actions['agent_0']", torch.int32, (T, n))
+            a1 = self._check(actions["agent_1"], "actions['agent_1']", torch.int32, (T, n))
+            io.act0, io.act1 = a0.data_ptr(), a1.data_ptr()
+        out = dict(out) if out is not None else {}
+        img = (h, w, N_CHANNELS)
+        if out.get("obs0") is not None:
+            obs0 = self._check(out["obs0"], "out['obs0']", torch.uint8, (T, n) + img)
+            obs1 = self._check(out["obs1"], "out['obs1']", torch.uint8, (T, n) + img)
+            if T > 1 and obs0.stride(0) != obs1.stride(0):
+                raise ValueError("out['obs0'] and out['obs1'] need the same step stride")
+            stride = n * h * w * N_CHANNELS
+        else:
+            obs = out.get("obs")
+            if obs is None:
+                obs = torch.empty((T, 2, n) + img, dtype=torch.uint8, device=dev)
+            self._check(obs, "out['obs']", torch.uint8, (T, 2, n) + img)
+            obs0, obs1 = obs[:, 0], obs[:, 1]
+            stride = 2 * n * h * w * N_CHANNELS
+        io.obs0, io.obs1, io.obs_step_stride = obs0.data_ptr(), obs1.data_ptr(), stride
+        res8 = out.get("results8")
+        reward = sh0 = sh1 = done = None
+        if res8 is not None:
+            self._check(res8, "out['results8']", torch.uint8, (T, n))
+            io.results8 = res8.data_ptr()
+        else:
+            reward = out.get("reward") if out.get("reward") is not None else torch.empty((T, n), dtype=torch.float32, device=dev)
+            sh0 = out.get("shaped0") if out.get("shaped0") is not None else torch.empty((T, n), dtype=torch.float32, device=dev)
+            sh1 = out.get("shaped1") if out.get("shaped1") is not None else torch.empty((T, n), dtype=torch.float32, device=dev)
+            done = out.get("done") if out.get("done") is not None else torch.empty((T, n), dtype=torch.bool, device=dev)
+            for k, t in (("reward", reward), ("shaped0", sh0), ("shaped1", sh1)):
+                self._check(t, f"out['{k}']", torch.float32, (T, n))
+            self._check(done, "out['done']", (torch.bool, torch.uint8), (T, n))
+            io.reward, io.shaped0, io.shaped1, io.done = reward.data_ptr(), sh0.data_ptr(), sh1.data_ptr(), done.data_ptr()
+        if out.get("cells") is not None:
+            self._check(out["cells"], "out['cells']", torch.uint8, (T, n, self.info.cell_stride))
+            e.cells = out["cells"].data_ptr()
+        if log is not None:
+            for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths"):
+                if log.get(f) is None:
+                    raise ValueError(f"log['{f}'] is missing: the four LogWrapper trackers go together")
+                setattr(e, f, self._check(log[f], f"log['{f}']", torch.float32, (n, 2)).data_ptr())
+            if log.get("returned_episode") is not None:
+                e.returned_episode = self._check(log["returned_episode"], "log['returned_episode']",
+                                                 (torch.bool, torch.uint8), (T, n, 2)).data_ptr()
+        if stats is not None:
+            e.stats = self._check(stats, "stats", torch.int64, (8,)).data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.oc_rollout(self._handle, n, T, key_ptr, sp, C.byref(io), C.byref(e), self._stream()),
+                       "oc_rollout")
+        obs_d = {"agent_0": obs0, "agent_1": obs1}
+        if res8 is not None:
+            return obs_d, state, {"results8": res8}, {"results8": res8}, {"results8": res8}
+        rewards = {"agent_0": reward, "agent_1": reward}
+        dones = {"agent_0": done, "agent_1": done, "__all__": done}
+        infos = {"shaped_reward": {"agent_0": sh0, "agent_1": sh1}}
+        return obs_d, state, rewards, dones, infos
+
+    @staticmethod
+    def unpack_results8(res8):
+        """Decode the packed results of `rollout(out={"results8": ...})` / HostRollout(packed=True):
+        (reward f32, shaped0 f32, shaped1 f32, done bool), same shape as `res8` (torch tensor or numpy array)."""
+        lut = res8.new_tensor([0.0, 3.0, 5.0, 0.0], dtype=torch.float32) if torch.is_tensor(res8) else np.array([0, 3, 5, 0], np.float32)
+        r = res8.to(torch.int64) if torch.is_tensor(res8) else res8.astype(np.int64)
+        reward = (r & 3) * 20
+        reward = reward.to(torch.float32) if torch.is_tensor(res8) else reward.astype(np.float32)
+        return reward, lut[(r >> 2) & 3], lut[(r >> 4) & 3], ((r >> 6) & 1) != 0
+
     # ------------------------------------------------------------------ host-policy fast path
     def host_stepper(self, state, n_global=None, first=0, stream=None):
         """Bind one env batch for repeated `oc_step_host` calls: actions arrive in pinned host memory, rewards /
@@ -448,6 +556,80 @@ class HostStepper:
         rc = self._wait(self._h)
         if rc:
             _lib.check(rc, "oc_host_stepper_wait")
+
+
+class HostRollout:
+    """One env batch bound to `oc_rollout_host` (include/oc_b200.h): ONE C call enqueues the host-to-device copy of T steps'
+    actions, one T-step launch and the device-to-host copy of the T steps' results on this batch's stream.
+      packed=False (reference dtypes): `actions` pinned int32[2, T, N]; results pinned views reward / shaped0 / shaped1
+                   float32[T, N], done bool[T, N] -- 21 bytes per env-step over PCIe
+      packed=True:  `actions` pinned uint8[T, N] (agent_0 | agent_1 << 4); `results8` pinned uint8[T, N]
+                   (Overcooked.unpack_results8) -- 2 bytes per env-step
+    Observations stay on the device in `obs` uint8[T, 2, N, h, w, 26] (the learners' layout); step t's per-env keys are
+    split(keys[t], n_global)[first + i], derived in the kernel."""
+
+    def __init__(self, env, state, num_steps, n_global=None, first=0, stream=None, packed=False, obs=None):
+        batch = tuple(state.time.shape)
+        if len(batch) != 1 or (batch[0] * num_steps) % 4:
+            raise ValueError("HostRollout needs a 1-D batch with num_steps * N a multiple of 4")
+        self.env, self.state, self.n, self.T, self.packed = env, state, batch[0], int(num_steps), bool(packed)
+        self.n_global = self.n if n_global is None else int(n_global)
+        self.first = int(first)
+        n, T, dev = self.n, self.T, env.device
+        self.stream = torch.cuda.Stream(dev) if stream is None else stream
+        if packed:
+            self.actions = torch.zeros((T, n), dtype=torch.uint8).pin_memory()
+            self.results8 = torch.zeros((T, n), dtype=torch.uint8).pin_memory()
+            self._results = self.results8
+            self._scratch = torch.empty(2 * T * n + 16, dtype=torch.uint8, device=dev)
+        else:
+            self.actions = torch.zeros((2, T, n), dtype=torch.int32).pin_memory()
+            self._results = torch.zeros(13 * T * n, dtype=torch.uint8).pin_memory()
+            tn = T * n
+            self.reward = self._results[:4 * tn].view(torch.float32).view(T, n)
+            self.shaped0 = self._results[4 * tn:8 * tn].view(torch.float32).view(T, n)
+            self.shaped1 = self._results[8 * tn:12 * tn].view(torch.float32).view(T, n)
+            self.done = self._results[12 * tn:].view(torch.bool).view(T, n)
+            self._scratch = torch.empty(21 * T * n + 16, dtype=torch.uint8, device=dev)
+        img = (env.height, env.width, N_CHANNELS)
+        self.obs = torch.empty((T, 2, n) + img, dtype=torch.uint8, device=dev) if obs is None else env._check(
+            obs, "obs", torch.uint8, (T, 2, n) + img)
+        self._sp = env._state_ptrs(state, batch)
+        self._ex = _lib.StepExtras()
+        self._ex.split_num, self._ex.split_first = self.n_global, self.first
+        self._stride = 2 * n * env.height * env.width * N_CHANNELS
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        self._call = env._lib.oc_rollout_host
+
+    def run(self, keys, actions=None, log=None, stats=None):
+        """Enqueue T steps.  keys: uint32[T, 2] CUDA tensor (the T per-step subkeys); `actions`: a pinned host tensor to use
+        instead of `self.actions`."""
+        env, T, n = self.env, self.T, self.n
+        act = self.actions if actions is None else actions
+        want = ((T, n), torch.uint8) if self.packed else ((2, T, n), torch.int32)
+        if (not torch.is_tensor(act) or tuple(act.shape) != want[0] or act.dtype != want[1] or not act.is_contiguous()
+                or act.device.type != "cpu" or not act.is_pinned()):
+            raise ValueError(f"actions must be a contiguous pinned {want[1]} host tensor of shape {want[0]}")
+        if (not torch.is_tensor(keys) or keys.dtype != torch.uint32 or tuple(keys.shape) != (T, 2) or keys.device != env.device
+                or not keys.is_contiguous()):
+            raise ValueError("keys must be a contiguous uint32[T, 2] tensor on the env's device")
+        env._check_log(None if log is None else {k: v for k, v in log.items() if k != "returned_episode"}, stats, (n,))
+        ex = self._ex
+        ex.split_key = keys.data_ptr()
+        if log is not None:
+            for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths"):
+                setattr(ex, f, log[f].data_ptr())
+        ex.stats = stats.data_ptr() if stats is not None else None
+        self._keepalive = (keys, act, log, stats)
+        with torch.cuda.device(env.device):
+            rc = self._call(env._handle, n, T, self._sp, _lib.WIRE_PACKED if self.packed else _lib.WIRE_REFERENCE,
+                            act.data_ptr(), self._results.data_ptr(), self._scratch.data_ptr(), self.obs[:, 0].data_ptr(),
+                            self.obs[:, 1].data_ptr(), self._stride, C.byref(ex), C.c_void_p(self.stream.cuda_stream))
+        if rc:
+            _lib.check(rc, "oc_rollout_host")
+
+    def wait(self):
+        self.stream.synchronize()
 
 
 registered_envs = ["overcooked"]

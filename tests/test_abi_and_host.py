@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"liboc_b200.so does not export {name}"
     lib.oc_version.restype = ctypes.c_int
-    assert lib.oc_version() == 110
+    assert lib.oc_version() == 120
     lib.oc_status_string.restype = ctypes.c_char_p
     assert lib.oc_status_string(-2) == b"unsupported layout"
 
@@ -33,7 +33,7 @@ def test_binding_covers_header():
     declared = set(re.findall(r"\b(oc_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS)
     lib = _lib.load()
-    assert lib.oc_version() == 110
+    assert lib.oc_version() == 120
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -1,0 +1,213 @@
+"""oc_rollout (T steps per launch, state resident on chip) against T oc_step calls AND against the CPU oracle, through the
+C ABI.  Bit-exact for every State field, both observations of every step, rewards, shaped rewards, dones, the LogWrapper
+trackers, the statistics and the compact observations; both key forms, both action / result wire formats."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import LOG_FIELDS, assert_same
+
+pytestmark = pytest.mark.gpu
+
+ACTION_P = np.array([0.15, 0.15, 0.15, 0.15, 0.05, 0.35])
+
+
+def _mods():
+    import jaxovercooked_b200 as ocb
+    from jaxovercooked_b200 import random as ocr
+    from oracle import oracle as orc
+    from tests import gpu_helpers as gh
+    return ocb, ocr, orc, gh
+
+
+def _setup(layout_name, N, T, seed, *, random_reset=False, max_steps=13, part=False, time_offsets=True, padded=False):
+    ocb, ocr, orc, gh = _mods()
+    lay = ocb.overcooked_layouts[layout_name]
+    if padded:
+        from jaxovercooked_b200.layouts import cl_sequence_padded
+        lay = cl_sequence_padded()[layout_name]
+    impl = "threefry_partitionable" if part else "threefry_legacy"
+    env = ocb.make("overcooked", layout=lay, random_reset=random_reset, max_steps=max_steps, prng_impl=impl)
+    ref = orc.Oracle(lay, random_reset=random_reset, max_steps=max_steps, partitionable=part)
+    rng = np.random.default_rng(seed)
+    rk = rng.integers(0, 2**32, (N, 2), dtype=np.uint32)
+    _, st = env.reset(gh.keys_to_dev(rk))
+    _, rst = ref.reset(rk)
+    if time_offsets:
+        off = rng.integers(0, max_steps, N).astype(np.int32)
+        rst["time"][:] = off
+        st.time.copy_(gh.to_dev(off))
+    a = rng.choice(6, size=(T, N, 2), p=ACTION_P).astype(np.int32)
+    return env, ref, st, rst, rng, a, impl
+
+
+@pytest.mark.parametrize("layout_name,N,T,random_reset,part,padded", [
+    ("cramped_room", 64, 20, False, False, False),
+    ("cramped_room", 37, 33, True, False, False),        # ragged last tile: plain-store path
+    ("cramped_room", 1000, 16, True, True, False),
+    ("cramped_room", 1, 7, False, False, False),
+    ("forced_coord", 130, 24, True, False, False),
+    ("coord_ring", 96, 24, False, False, True),           # 5 x 9 padded CL layout
+    ("counter_circuit", 250, 18, True, True, False),
+    ("easy_layout_padded", 77, 15, True, False, False),   # 10 x 10: static image pulled by the bulk-copy engine
+    ("bottleneck_large", 40, 15, True, False, False),
+    ("smallest_kitchen", 513, 12, True, False, False),
+])
+def test_rollout_matches_oracle_and_steps(layout_name, N, T, random_reset, part, padded):
+    """Explicit per-step per-env keys u32[T, N, 2]: every step of the rollout against the oracle, final state against both."""
+    ocb, ocr, orc, gh = _mods()
+    env, ref, st, rst, rng, a, impl = _setup(layout_name, N, T, 11, random_reset=random_reset, part=part, padded=padded)
+    sk = rng.integers(0, 2**32, (T, N, 2), dtype=np.uint32)
+    st_steps = st.clone()
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    cells = torch.zeros((T, N, env.info.cell_stride), dtype=torch.uint8, device="cuda")
+    obs, st2, rew, done, info = env.rollout(gh.keys_to_dev(sk), st, acts, out={"cells": cells})
+    assert st2 is st
+    torch.cuda.synchronize()
+    o0, o1 = obs["agent_0"].cpu().numpy(), obs["agent_1"].cpu().numpy()
+    for t in range(T):
+        (r0, r1), rr, s0, s1, dd = ref.step(sk[t], rst, a[t, :, 0], a[t, :, 1])
+        assert_same(o0[t], r0, f"t={t} obs0")
+        assert_same(o1[t], r1, f"t={t} obs1")
+        assert_same(rew["agent_0"][t].cpu().numpy(), rr, f"t={t} reward")
+        assert_same(info["shaped_reward"]["agent_0"][t].cpu().numpy(), s0, f"t={t} shaped0")
+        assert_same(info["shaped_reward"]["agent_1"][t].cpu().numpy(), s1, f"t={t} shaped1")
+        assert_same(done["__all__"][t].cpu().numpy(), dd, f"t={t} done")
+        # the same steps one launch at a time
+        c1 = env.empty_cells(N)
+        ob, st_steps, rw, dn, inf = env.step(gh.keys_to_dev(sk[t]), st_steps, {"agent_0": acts["agent_0"][t], "agent_1": acts["agent_1"][t]},
+                                             donate=True, out=None)
+        env.get_obs(st_steps, cells=c1)
+        assert_same(cells[t].cpu().numpy(), c1.cpu().numpy(), f"t={t} cells")
+        assert torch.equal(ob["agent_0"], obs["agent_0"][t]) and torch.equal(ob["agent_1"], obs["agent_1"][t])
+    gh.compare_state(st, rst, "after the rollout")
+    gh.compare_state(st_steps, rst, "after T steps")
+
+
+@pytest.mark.parametrize("part", [False, True])
+def test_rollout_fused_keys_log_and_stats(part):
+    """Keys as the T per-step subkeys u32[T, 2] (split per env in the kernel), LogWrapper trackers carried in registers,
+    statistics summed over the T steps; against T single steps with the LogWrapper."""
+    ocb, ocr, orc, gh = _mods()
+    N, T = 300, 40
+    env, ref, st, rst, rng, a, impl = _setup("cramped_room", N, T, 5, random_reset=True, part=part, max_steps=11)
+    wenv = ocb.LogWrapper(env)
+    keys = ocr.split_chain(ocr.PRNGKey(3), T, impl=impl)
+    log_a = {f: torch.zeros((N, 2), dtype=torch.float32, device="cuda") for f in LOG_FIELDS}
+    log_a["returned_episode"] = torch.zeros((T, N, 2), dtype=torch.bool, device="cuda")
+    stats_a = torch.zeros(8, dtype=torch.int64, device="cuda")
+    st_b = st.clone()
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs, _, rew, done, info = env.rollout(keys, st, acts, log=log_a, stats=stats_a)
+    # reference: T single LogWrapper steps with materialised split(keys[t], N)
+    log_b = {f: torch.zeros((N, 2), dtype=torch.float32, device="cuda") for f in LOG_FIELDS}
+    stats_b = torch.zeros(8, dtype=torch.int64, device="cuda")
+    for t in range(T):
+        kt = ocr.split(keys[t], N, impl=impl)
+        re_b = torch.zeros((N, 2), dtype=torch.bool, device="cuda")
+        lb = dict(log_b, returned_episode=re_b)
+        ob, st_b, rw, dn, inf = env.step(kt, st_b, {"agent_0": acts["agent_0"][t], "agent_1": acts["agent_1"][t]}, donate=True,
+                                         log=lb, stats=stats_b)
+        assert torch.equal(ob["agent_0"], obs["agent_0"][t]) and torch.equal(ob["agent_1"], obs["agent_1"][t]), f"obs t={t}"
+        assert torch.equal(rw["agent_0"], rew["agent_0"][t]) and torch.equal(dn["__all__"], done["__all__"][t])
+        assert torch.equal(inf["shaped_reward"]["agent_1"], info["shaped_reward"]["agent_1"][t])
+        assert torch.equal(re_b, log_a["returned_episode"][t]), f"returned_episode t={t}"
+        # and the oracle, with the same materialised keys
+        (r0, r1), rr, s0, s1, dd = ref.step(kt.cpu().numpy(), rst, a[t, :, 0], a[t, :, 1])
+        assert_same(obs["agent_0"][t].cpu().numpy(), r0, f"t={t} obs0 vs oracle")
+    for f in LOG_FIELDS:
+        assert torch.equal(log_a[f], log_b[f]), f
+    assert torch.equal(stats_a, stats_b), (stats_a.tolist(), stats_b.tolist())
+    assert int(stats_a[6]) == N * T and int(stats_a[0]) > 0
+    gh.compare_state(st, rst, "after the rollout")
+
+
+def test_rollout_packed_wire_format_and_separate_views():
+    """actions u8[T, N] in, results u8[T, N] out, obs0 / obs1 as two [T, N, ...] tensors."""
+    ocb, ocr, orc, gh = _mods()
+    N, T = 512, 60
+    env, ref, st, rst, rng, a, impl = _setup("cramped_room", N, T, 9, random_reset=True, max_steps=25)
+    keys = ocr.split_chain(ocr.PRNGKey(8), T)
+    st_b = st.clone()
+    a8 = gh.to_dev((a[:, :, 0] | (a[:, :, 1] << 4)).astype(np.uint8))
+    res8 = torch.zeros((T, N), dtype=torch.uint8, device="cuda")
+    o0 = torch.zeros((T, N, env.height, env.width, 26), dtype=torch.uint8, device="cuda")
+    o1 = torch.zeros_like(o0)
+    env.rollout(keys, st, a8, out={"results8": res8, "obs0": o0, "obs1": o1})
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs, _, rew, done, info = env.rollout(keys, st_b, acts)
+    r, s0, s1, d = env.unpack_results8(res8)
+    assert torch.equal(r, rew["agent_0"]) and torch.equal(d, done["__all__"])
+    assert torch.equal(s0, info["shaped_reward"]["agent_0"]) and torch.equal(s1, info["shaped_reward"]["agent_1"])
+    assert torch.equal(o0, obs["agent_0"]) and torch.equal(o1, obs["agent_1"])
+    assert float(r.sum()) > 0 and float(s0.sum()) > 0 and int(d.sum()) > 0     # the interesting values occurred
+    for f in ("agent_pos", "agent_inv", "maze_map", "time"):
+        assert torch.equal(getattr(st, f), getattr(st_b, f)), f
+
+
+def test_rollout_t1_equals_step_and_errors():
+    ocb, ocr, orc, gh = _mods()
+    N = 50
+    env, ref, st, rst, rng, a, impl = _setup("cramped_room", N, 1, 2)
+    sk = rng.integers(0, 2**32, (1, N, 2), dtype=np.uint32)
+    st_b = st.clone()
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs, _, rew, done, info = env.rollout(gh.keys_to_dev(sk), st, acts)
+    ob, st_b, rw, dn, inf = env.step(gh.keys_to_dev(sk[0]), st_b, {"agent_0": acts["agent_0"][0], "agent_1": acts["agent_1"][0]}, donate=True)
+    assert torch.equal(ob["agent_0"], obs["agent_0"][0]) and torch.equal(rw["agent_0"], rew["agent_0"][0])
+    assert torch.equal(st.maze_map, st_b.maze_map)
+    with pytest.raises(ValueError):
+        env.rollout(gh.keys_to_dev(sk), st, {"agent_0": acts["agent_0"][:, :10], "agent_1": acts["agent_1"]})
+    with pytest.raises(ValueError):
+        env.rollout(gh.keys_to_dev(sk)[:, :, :1].contiguous(), st, acts)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_host_rollout_matches_device_rollout(packed):
+    """oc_rollout_host (host actions in, host results out, one copy each way per T steps) against oc_rollout."""
+    ocb, ocr, orc, gh = _mods()
+    N, T = 512, 16
+    env, ref, st, rst, rng, a, impl = _setup("cramped_room", N, T, 21, random_reset=True, max_steps=10)
+    st_b = st.clone()
+    keys = ocr.split_chain(ocr.PRNGKey(4), T)
+    hr = ocb.HostRollout(env, st, T, packed=packed)
+    if packed:
+        hr.actions.copy_(torch.from_numpy((a[:, :, 0] | (a[:, :, 1] << 4)).astype(np.uint8)))
+    else:
+        hr.actions.copy_(torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))))
+    torch.cuda.synchronize()
+    hr.run(keys)
+    hr.wait()
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs, _, rew, done, info = env.rollout(keys, st_b, acts)
+    torch.cuda.synchronize()
+    if packed:
+        r, s0, s1, d = env.unpack_results8(hr.results8)
+    else:
+        r, s0, s1, d = hr.reward, hr.shaped0, hr.shaped1, hr.done
+    assert torch.equal(r, rew["agent_0"].cpu()) and torch.equal(d, done["__all__"].cpu())
+    assert torch.equal(s0, info["shaped_reward"]["agent_0"].cpu()) and torch.equal(s1, info["shaped_reward"]["agent_1"].cpu())
+    assert torch.equal(hr.obs[:, 0], obs["agent_0"]) and torch.equal(hr.obs[:, 1], obs["agent_1"])
+    assert torch.equal(st.maze_map, st_b.maze_map) and torch.equal(st.time, st_b.time)
+
+
+def test_rollout_full_size_properties():
+    """BASELINE configs[1] size: 65,536 cramped_room envs x 32 steps in one launch equals 32 single-step launches, bit for bit."""
+    ocb, ocr, orc, gh = _mods()
+    N, T = 65536, 32
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"], max_steps=400)
+    _, st = env.reset(ocr.split(ocr.PRNGKey(0), N))
+    st.time.copy_(torch.randint(0, 400, (N,), dtype=torch.int32, device="cuda"))
+    st_b = st.clone()
+    keys = ocr.split_chain(ocr.PRNGKey(1), T)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = {"agent_0": torch.randint(0, 6, (T, N), dtype=torch.int32, device="cuda", generator=g),
+            "agent_1": torch.randint(0, 6, (T, N), dtype=torch.int32, device="cuda", generator=g)}
+    obs, _, rew, done, info = env.rollout(keys, st, acts)
+    for t in range(T):
+        ob, st_b, rw, dn, inf = env.step(ocr.LazySplit(keys[t], N), st_b, {"agent_0": acts["agent_0"][t], "agent_1": acts["agent_1"][t]}, donate=True)
+        assert torch.equal(ob["agent_0"], obs["agent_0"][t]) and torch.equal(ob["agent_1"], obs["agent_1"][t]), f"t={t}"
+        assert torch.equal(rw["agent_0"], rew["agent_0"][t]) and torch.equal(dn["__all__"], done["__all__"][t])
+    for f in ("agent_pos", "agent_dir", "agent_dir_idx", "agent_inv", "maze_map", "time", "terminal"):
+        assert torch.equal(getattr(st, f), getattr(st_b, f)), f
+    assert int(done["__all__"].sum()) > 0
