@@ -120,7 +120,14 @@ typedef struct {
      * this instead of re-reading the 26-channel images.  The buffer must be 16-byte aligned (OC_ERR_ALIGNMENT); padding
      * bytes of a row are written as 0xFF. */
     uint8_t *cells;
+    /* Observation layout.  0: obs0 / obs1 are two uint8[N,h,w,26] arrays (default).  1 (OC_OBS_INTERLEAVED): obs0 points at
+     * ONE uint8[N,2,h,w,26] array -- agent_0's and agent_1's view of an env side by side, which flattened per env is the
+     * CTRolloutManager's global state obs["__all__"] (wrappers/baselines.py:196: concatenate([obs[a].flatten() for a in
+     * agents])) while [:,0] / [:,1] are the per-agent observations; obs1 must be NULL or obs0 + h*w*26.  The array must be
+     * 16-byte aligned for the bulk-copy path; not combinable with `cells`. */
+    int32_t obs_interleaved;
 } oc_step_extras;
+#define OC_OBS_INTERLEAVED 1
 
 typedef struct {
     int32_t height, width, n_goal, n_pot;
@@ -210,6 +217,7 @@ typedef struct {
     float *reward, *shaped0, *shaped1;
     uint8_t *done;
     uint8_t *results8;
+    int32_t obs_interleaved;   /* as oc_step_extras.obs_interleaved; step t's uint8[N,2,h,w,26] starts at obs0 + t*obs_step_stride */
 } oc_rollout_io;
 
 int oc_rollout(const oc_layout *layout, int64_t N, int32_t T, const uint32_t *keys, oc_state state,
@@ -231,6 +239,9 @@ int oc_get_obs(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, u
 /* ... and their compact form as well (see oc_step_extras.cells): what a rollout needs right after oc_reset. */
 int oc_get_obs_cells(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, uint8_t *cells,
                      void *stream);
+/* ... as ONE uint8[N,2,h,w,26] array (oc_step_extras.obs_interleaved): what CTRolloutManager.batch_reset returns as
+ * obs["__all__"] (wrappers/baselines.py:217) with the per-agent observations as its [:,0] / [:,1] slices. */
+int oc_get_obs_all(const oc_layout *layout, int64_t N, oc_state in, uint8_t *obs_all, void *stream);
 /* Decoding tables of the compact form, into HOST memory (either may be NULL): the 26-byte record of every cell code
  * (uint8[OC_NUM_CELL_CODES][26], as agent_0 sees it) and the cell index of every scan cell (int32[n_scan]). */
 int oc_layout_cell_tables(const oc_layout *layout, uint8_t *records, int32_t *scan_cells);

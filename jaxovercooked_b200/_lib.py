@@ -37,7 +37,8 @@ class StatePtrs(C.Structure):
 
 class StepExtras(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in EXTRA_FIELDS] + [("split_key", C.c_void_p), ("split_num", C.c_int64),
-                                                          ("split_first", C.c_int64), ("cells", C.c_void_p)]
+                                                          ("split_first", C.c_int64), ("cells", C.c_void_p),
+                                                          ("obs_interleaved", C.c_int32)]
 
 
 class LayoutInfo(C.Structure):
@@ -51,7 +52,7 @@ class LayoutInfo(C.Structure):
 class RolloutIO(C.Structure):
     _fields_ = [("act0", C.c_void_p), ("act1", C.c_void_p), ("actions8", C.c_void_p), ("obs0", C.c_void_p),
                 ("obs1", C.c_void_p), ("obs_step_stride", C.c_int64), ("reward", C.c_void_p), ("shaped0", C.c_void_p),
-                ("shaped1", C.c_void_p), ("done", C.c_void_p), ("results8", C.c_void_p)]
+                ("shaped1", C.c_void_p), ("done", C.c_void_p), ("results8", C.c_void_p), ("obs_interleaved", C.c_int32)]
 
 
 WIRE_REFERENCE, WIRE_PACKED = 0, 1
@@ -65,7 +66,7 @@ class PolicyDesc(C.Structure):
 
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
            "oc_reset", "oc_step", "oc_rollout", "oc_rollout_host", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
-           "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_prng_split", "oc_prng_chain",
+           "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_get_obs_all", "oc_prng_split", "oc_prng_chain",
            "oc_policy_create", "oc_policy_update", "oc_policy_destroy", "oc_policy_forward", "oc_policy_forward_cells", "oc_policy_sample",
            "oc_layout_obs_template", "oc_get_obs_cells", "oc_layout_cell_tables")
 
@@ -101,6 +102,8 @@ def load():
     lib.oc_reset.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oc_get_obs.restype = C.c_int
     lib.oc_get_obs.argtypes = [C.c_void_p, C.c_int64, StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oc_get_obs_all.restype = C.c_int
+    lib.oc_get_obs_all.argtypes = [C.c_void_p, C.c_int64, StatePtrs, C.c_void_p, C.c_void_p]
     lib.oc_step.restype = C.c_int
     lib.oc_step.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, StatePtrs, C.c_void_p, C.c_void_p,
                             C.POINTER(StatePtrs), StatePtrs, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -118,23 +118,31 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     if (kp.n_tiles < 1) return OC_OK;
     const bool with_cells = kp.cells != nullptr;
     if (with_cells && !aligned16(kp.cells)) return OC_ERR_ALIGNMENT;
-    void (*kern)(const KParams) = with_cells ? oc_env_kernel<MODE, true> : oc_env_kernel<MODE, false>;
+    if (kp.interleaved && (with_cells || lay->epw < 2 || MODE == MODE_RESET)) return OC_ERR_INVALID_ARG;
+    const int var = kp.interleaved ? VAR_ALL : (with_cells ? VAR_CELLS : VAR_PLAIN);
+    void (*kern)(const KParams) = kp.interleaved ? oc_env_kernel<MODE, (MODE == MODE_RESET) ? VAR_PLAIN : VAR_ALL>
+                                  : (with_cells ? oc_env_kernel<MODE, VAR_CELLS> : oc_env_kernel<MODE, VAR_PLAIN>);
     // the compact observations of a tile are staged per warp, behind the warp's regular shared-memory area
     const int cells_smem = with_cells ? lay->epw * lay->cell_stride : 0;
-    const int smem_bytes = lay->smem_bytes + lay->warps * cells_smem;
+    // MODE_ROLLOUT keeps one span buffer per warp instead of two (oc_kernels.cuh: SPAN_BUFS)
+    const int warp_bytes0 = lay->warp_bytes - (MODE == MODE_ROLLOUT ? lay->epw * H.span_stride : 0);
+    const int smem_bytes0 = lay->smem_bytes - lay->warps * (lay->warp_bytes - warp_bytes0) + lay->warps * cells_smem;
+    const int act_smem = (MODE == MODE_ROLLOUT) ? 4 * 32 * 4 : 0;   // oc_kernels.cuh: ACT_RING slots of 32 lanes
+    const int smem_bytes = smem_bytes0 + lay->warps * act_smem;
     if (smem_bytes > 227 * 1024) return OC_ERR_UNSUPPORTED_LAYOUT;
-    kp.cells_off = lay->warp_bytes;
-    kp.warp_bytes = lay->warp_bytes + cells_smem;
-    if (lay->occ[MODE + (with_cells ? NUM_MODES : 0)] == 0) {
+    kp.act_off = warp_bytes0;
+    kp.cells_off = warp_bytes0 + act_smem;
+    kp.warp_bytes = warp_bytes0 + act_smem + cells_smem;
+    if (lay->occ[MODE + var * NUM_MODES] == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, smem_bytes) != cudaSuccess)
             return fail_cuda();
-        lay->occ[MODE + (with_cells ? NUM_MODES : 0)] = nb < 1 ? 1 : nb;
+        lay->occ[MODE + var * NUM_MODES] = nb < 1 ? 1 : nb;
     }
     // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
-    const long long resident = (long long)lay->num_sms * lay->occ[MODE + (with_cells ? NUM_MODES : 0)];
+    const long long resident = (long long)lay->num_sms * lay->occ[MODE + var * NUM_MODES];
     const long long want = (kp.n_tiles + lay->warps - 1) / lay->warps;
     long long ctas = want;
     if (want > resident) {
@@ -344,7 +352,7 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->num_sms = prop.multiProcessorCount;
     lay->cell_agents = (L.n_scan + 1) & ~1;
     lay->cell_stride = (lay->cell_agents + 5 + 15) & ~15;
-    for (int i = 0; i < 2 * NUM_MODES; ++i) lay->occ[i] = 0;
+    for (int i = 0; i < NUM_VARS * NUM_MODES; ++i) lay->occ[i] = 0;
     lay->device = device;
     {   // tile-sized static observation image
         const size_t eb = (size_t)C * OC_OBS_CHANNELS;
@@ -419,6 +427,17 @@ int oc_get_obs(const oc_layout *lay, int64_t N, oc_state in, uint8_t *obs0, uint
     return oc_get_obs_cells(lay, N, in, obs0, obs1, nullptr, stream_);
 }
 
+int oc_get_obs_all(const oc_layout *lay, int64_t N, oc_state in, uint8_t *obs_all, void *stream_) {
+    if (!lay || N < 0 || !state_ok(in) || !obs_all) return OC_ERR_INVALID_ARG;
+    if (N == 0) return OC_OK;
+    if (!state_aligned(in)) return OC_ERR_ALIGNMENT;
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.N = N; kp.st = in; kp.obs0 = obs_all; kp.obs1 = obs_all + (size_t)lay->host.C * OC_OBS_CHANNELS; kp.interleaved = 1;
+    kp.bulk_ok = aligned16(obs_all);
+    return launch_env<MODE_OBS>(lay, kp, static_cast<cudaStream_t>(stream_));
+}
+
 int oc_get_obs_cells(const oc_layout *lay, int64_t N, oc_state in, uint8_t *obs0, uint8_t *obs1, uint8_t *cells,
                      void *stream_) {
     if (!lay || N < 0 || !state_ok(in) || !obs0 || !obs1) return OC_ERR_INVALID_ARG;
@@ -435,8 +454,12 @@ int oc_step(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state in, 
             const int32_t *act1, const oc_state *reset_state, oc_state out, uint8_t *obs0, uint8_t *obs1,
             float *reward, float *shaped0, float *shaped1, uint8_t *done, const oc_step_extras *extras,
             void *stream_) {
-    if (!lay || N < 0 || !state_ok(in) || !state_ok(out) || !act0 || !act1 || !obs0 || !obs1 || !reward ||
+    const bool inter = extras && extras->obs_interleaved;
+    if (!lay || N < 0 || !state_ok(in) || !state_ok(out) || !act0 || !act1 || !obs0 || (!obs1 && !inter) || !reward ||
         !shaped0 || !shaped1 || !done)
+        return OC_ERR_INVALID_ARG;
+    if (inter && ((extras->obs_interleaved != OC_OBS_INTERLEAVED) || extras->cells ||
+                  (obs1 && obs1 != obs0 + (size_t)lay->host.C * OC_OBS_CHANNELS)))
         return OC_ERR_INVALID_ARG;
     if (!keys && !(extras && extras->split_key && extras->split_num >= 1 && extras->split_first >= 0 &&
                    extras->split_first + N <= extras->split_num && extras->split_num <= 0x7fffffffll))
@@ -472,7 +495,8 @@ int oc_step(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state in, 
     kp.reward = reward; kp.shaped0 = shaped0; kp.shaped1 = shaped1; kp.done = done;
     if (reset_state) { kp.rs = *reset_state; kp.has_rs = 1; }
     if (extras) { kp.ex = *extras; kp.cells = extras->cells; }
-    kp.bulk_ok = aligned16(obs0) && aligned16(obs1);
+    kp.interleaved = inter ? 1 : 0;
+    kp.bulk_ok = aligned16(obs0) && (inter || aligned16(obs1));
     return launch_env<MODE_STEP>(lay, kp, stream);
 }
 
@@ -496,13 +520,17 @@ int oc_step_host(const oc_layout *lay, int64_t N, const uint32_t *keys, oc_state
 
 int oc_rollout(const oc_layout *lay, int64_t N, int32_t T, const uint32_t *keys, oc_state st, const oc_rollout_io *io,
                const oc_step_extras *extras, void *stream_) {
-    if (!lay || N < 0 || T < 1 || T > 65535 || !io || !state_ok(st) || !io->obs0 || !io->obs1) return OC_ERR_INVALID_ARG;
+    if (!lay || N < 0 || T < 1 || T > 65535 || !io || !state_ok(st) || !io->obs0 || (!io->obs1 && !io->obs_interleaved))
+        return OC_ERR_INVALID_ARG;
+    if (io->obs_interleaved && (io->obs_interleaved != OC_OBS_INTERLEAVED || (extras && extras->cells) ||
+                                (io->obs1 && io->obs1 != io->obs0 + (size_t)lay->host.C * OC_OBS_CHANNELS)))
+        return OC_ERR_INVALID_ARG;
     if (!io->actions8 && !(io->act0 && io->act1)) return OC_ERR_INVALID_ARG;
     if (!io->results8 && !(io->reward && io->shaped0 && io->shaped1 && io->done)) return OC_ERR_INVALID_ARG;
     if (!keys && !(extras && extras->split_key && extras->split_num >= 1 && extras->split_first >= 0 &&
                    extras->split_first + N <= extras->split_num && extras->split_num <= 0x7fffffffll))
         return OC_ERR_INVALID_ARG;
-    const long long view_bytes = (long long)N * lay->host.C * OC_OBS_CHANNELS;
+    const long long view_bytes = (long long)N * lay->host.C * OC_OBS_CHANNELS * (io->obs_interleaved ? 2 : 1);
     if (T > 1 && io->obs_step_stride < view_bytes) return OC_ERR_INVALID_ARG;
     if (N == 0) return OC_OK;
     if (!state_aligned(st) || (keys && !aligned_to(keys, 4)) || (io->act0 && !aligned_to(io->act0, 4)) ||
@@ -523,7 +551,8 @@ int oc_rollout(const oc_layout *lay, int64_t N, int32_t T, const uint32_t *keys,
     kp.obs0 = io->obs0; kp.obs1 = io->obs1; kp.obs_step_stride = io->obs_step_stride;
     kp.reward = io->reward; kp.shaped0 = io->shaped0; kp.shaped1 = io->shaped1; kp.done = io->done; kp.res8 = io->results8;
     if (extras) { kp.ex = *extras; kp.cells = extras->cells; }
-    kp.bulk_ok = aligned16(io->obs0) && aligned16(io->obs1) && (io->obs_step_stride % 16 == 0);
+    kp.interleaved = io->obs_interleaved ? 1 : 0;
+    kp.bulk_ok = aligned16(io->obs0) && (io->obs_interleaved || aligned16(io->obs1)) && (io->obs_step_stride % 16 == 0);
     return launch_env<MODE_ROLLOUT>(lay, kp, static_cast<cudaStream_t>(stream_));
 }
 

@@ -51,6 +51,7 @@ struct KParams {
     uint8_t *done;
     oc_step_extras ex;
     uint8_t *cells;       // compact observation (scan-cell codes, agent cells, urgency), or NULL
+    int act_off;    // MODE_ROLLOUT: the warp's action ring inside its shared memory
     int cell_stride, cell_agents, cells_off;   // cells_off: staging area inside the warp's shared memory (CELLS launches)
     int epw;        // environments per warp tile: 16, 8, 4 or 2
     int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
@@ -68,9 +69,11 @@ struct KParams {
     long long obs_step_stride;
     const uint8_t *act8;   // or NULL: packed actions u8[T, N], agent_0 | agent_1 << 4 (replaces act0 / act1)
     uint8_t *res8;         // or NULL: packed results u8[T, N] (oc_rollout_io.results8)
+    int interleaved;       // obs0 is uint8[N, 2, h, w, 26] (both views of an env side by side): launches the VAR_ALL instantiation
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBS = 2, MODE_ROLLOUT = 3, NUM_MODES = 4 };
+enum { VAR_PLAIN = 0, VAR_CELLS = 1, VAR_ALL = 2, NUM_VARS = 3 };   // oc_env_kernel<MODE, VAR>
 
 }  // namespace
 
@@ -87,6 +90,6 @@ struct oc_layout {
     unsigned char *tmpl_tile;
     int num_sms;
     int cell_stride, cell_agents;   // compact observation: bytes per env, offset of the agent entries (oc_step_extras.cells)
-    mutable int occ[2 * NUM_MODES];   // resident CTAs per SM of each kernel mode (filled on first launch)
+    mutable int occ[NUM_VARS * NUM_MODES];   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
 

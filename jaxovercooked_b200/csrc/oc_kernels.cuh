@@ -4,15 +4,38 @@
 #include "oc_rules.cuh"
 #include "threefry.cuh"
 
+#ifndef OC_OBS_EVICT_FIRST
+#define OC_OBS_EVICT_FIRST 0
+#endif
+#ifndef OC_ROLLOUT_MIN_CTAS
+#define OC_ROLLOUT_MIN_CTAS 7   // resident CTAs per SM the rollout instantiation is compiled for (72 registers)
+#endif
+
 namespace {
+
+// one bulk asynchronous copy shared -> global (the copy engine; SASS UBLKCP).  OC_OBS_EVICT_FIRST (tuning build): the
+// observation stream is marked evict-first in L2 so that it does not push the (re-read) action arrays out
+__device__ __forceinline__ void bulk_store(unsigned char *dst, uint32_t src_smem, int bytes) {
+#if OC_OBS_EVICT_FIRST
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(dst), "r"(src_smem), "r"(bytes), "l"(pol) : "memory");
+#else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------ kernel
 
 // CELLS: also emit the compact form of the observations (oc_step_extras.cells); a separate instantiation so that the
 // plain kernel keeps its register budget
-template <int MODE, bool CELLS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 : 8) oc_env_kernel(const __grid_constant__ KParams p) {
+template <int MODE, int VAR>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT || VAR == VAR_ALL) ? OC_ROLLOUT_MIN_CTAS : 8) oc_env_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
+    // VAR_CELLS: also emit the compact observations.  VAR_ALL: the two views of an env are written side by side
+    // (uint8[N, 2, h, w, 26], the CTRolloutManager's obs["__all__"], wrappers/baselines.py:196) instead of as two [N, h, w, 26] arrays
+    constexpr bool CELLS = (VAR == VAR_CELLS), INTERLEAVED = (VAR == VAR_ALL);
     const DevLayout *__restrict__ L = p.L;
     // ---- CTA-shared header: record table, wall/blocked bitmaps, pot cells, scan list, observation template
     // (the 68-entry record table stays in global memory: it is only touched for the few cells per env that deviate
@@ -35,9 +58,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
     const int view_bytes = epw * env_bytes;
     unsigned char *wbase = smem + kHdrFixed + p.scan_bytes + p.pf_bytes + p.tmpl_bytes + (size_t)warp * p.warp_bytes;
     unsigned char *stage = wbase;                                              // agent_0's view of the tile
-    unsigned char *smap_buf = wbase + view_bytes;                              // 2 x [epw][span_stride]
-    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + 2 * epw * span_stride);   // [2*epw] urgency flags
+    // the interior spans of the tile: double-buffered (the next tile is prefetched while this one is processed), except in
+    // MODE_ROLLOUT, where a tile stays for T steps and one buffer is enough -- the shared memory goes to occupancy instead
+    constexpr int SPAN_BUFS = (MODE == MODE_ROLLOUT) ? 1 : 2;
+    unsigned char *smap_buf = wbase + view_bytes;                              // SPAN_BUFS x [epw][span_stride]
+    uint32_t *s_ap = reinterpret_cast<uint32_t *>(smap_buf + SPAN_BUFS * epw * span_stride);   // [2*epw] urgency flags
     const uint32_t tbar = smem_u32(s_ap + 2 * epw);                                    // this warp's mbarrier (8 bytes)
+    // MODE_ROLLOUT: ring of the next steps' actions, one 32-bit slot per lane and step, filled by 4-byte cp.async three steps
+    // ahead (a register prefetch one step ahead measured 7 % slower at 65,536 envs: the int32 action loads miss L2)
+    constexpr int ACT_RING = 4;
+    uint32_t *s_act = reinterpret_cast<uint32_t *>(wbase + p.act_off);   // [ACT_RING][32]
     unsigned char *s_cells = wbase + p.cells_off;        // CELLS: [epw][cell_stride] staging of the compact observations
 
     const int e = lane >> 1, ai = lane & 1;   // env within the tile, agent index (0 = "Alice", 1 = "Bob")
@@ -167,7 +197,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
     Fields nf;
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
 
-    for (; tile < p.n_tiles; tile += tile_stride, buf ^= 1) {
+    for (; tile < p.n_tiles; tile += tile_stride, buf ^= (SPAN_BUFS - 1)) {
         const long long env0 = tile * epw;
         const int n_valid = (int)min((long long)epw, p.N - env0);
         const bool active = e < n_valid;
@@ -195,7 +225,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
         refill_stage();
         // ------------------------------------------------ (1)+(2) this tile's state; prefetch the next tile's
         const Fields cf = nf;
-        if (tile + tile_stride < p.n_tiles) {
+        if (SPAN_BUFS == 1) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if (tile + tile_stride < p.n_tiles) {
             prefetch_spans(tile + tile_stride, buf ^ 1);
             nf = load_fields(tile + tile_stride);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -209,11 +241,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
         int acc_done = 0, acc_rew = 0, acc_s0 = 0, acc_s1 = 0, acc_rr = 0, acc_rl = 0;   // MODE_ROLLOUT: statistics of the T steps
         __syncwarp();
 
+        const bool act_ring = (MODE == MODE_ROLLOUT) && !p.act8;
+        auto issue_act = [&](int ts2) {   // this lane's action of step ts2 -> its ring slot, asynchronously; one group per step
+            if (ts2 < T && active)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                             :: "r"(smem_u32(s_act + (ts2 & (ACT_RING - 1)) * 32 + lane)),
+                                "l"((ai ? p.act1 : p.act0) + (long long)ts2 * p.N + env) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (act_ring) { issue_act(1); issue_act(2); }
+
       for (int ts = 0; ts < T; ++ts) {
         const bool last_ts = (MODE != MODE_ROLLOUT) || ts == T - 1;
+        if (act_ring) issue_act(ts + 3);
         if (MODE == MODE_ROLLOUT && ts > 0) refill_stage();   // every step emits from a fresh static image
         int nact = 4;
-        if (MODE == MODE_ROLLOUT && !last_ts && active) nact = load_act(ts + 1, env);   // consumed a whole step later
+        if (MODE == MODE_ROLLOUT && !act_ring && !last_ts && active) nact = load_act(ts + 1, env);   // packed actions: register prefetch
         int nx = px, ny = py, ndi = di, ninv = inv, t_out = t, term_out = 0;
         bool done = (MODE == MODE_RESET);
         int rew = 0, shaped = 0;
@@ -389,8 +432,97 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
         // ---------------------------------------------------------------- (4) observations (overcooked.py:250-364)
         bool obs1_pending = false;
         int code_v1 = 0, my_cell = 0, urg_lane = 0;
-        const size_t obs_off = (size_t)env0 * env_bytes + ((MODE == MODE_ROLLOUT) ? (size_t)ts * (size_t)p.obs_step_stride : 0);
-        {
+        const size_t obs_off = (size_t)env0 * env_bytes * (INTERLEAVED ? 2 : 1) + ((MODE == MODE_ROLLOUT) ? (size_t)ts * (size_t)p.obs_step_stride : 0);
+        if (INTERLEAVED) {
+            // Both views of an env side by side: row e of the output is [agent_0's view | agent_1's view].  The staging image
+            // holds epw / 2 envs x 2 views, so a tile leaves in two halves, each one bulk copy of the usual size; a deviating
+            // scan cell is staged twice (once per view), the agent cells once per view with the viewer bit as that view sees it.
+            const int urg = (p.max_steps - t_out) < 40;                                       // :311
+            if (active) s_ap[lane] = (uint32_t)urg;
+            const int half = epw >> 1;
+            const int code_v0 = kCodeAgent + 16 * ai + (ndi | (inv_code(ninv) << 2));
+            for (int hf = 0; hf < 2; ++hf) {
+                const int e_lo = hf * half;
+                const int nv_h = min(half, n_valid - e_lo);
+                if (nv_h <= 0) break;
+                if (p.tmpl_bytes) {
+                    if (bulk_pending) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        bulk_pending = false;
+                        __syncwarp();
+                    }
+                    const int n_chunks = (2 * nv_h * env_bytes + 15) >> 4;
+                    uint4 *dst = reinterpret_cast<uint4 *>(stage);
+                    int src = lane;
+                    src -= (int)fastdiv((unsigned)src, p.magic_tc) * p.tmpl_chunks;
+                    const int step = 32 - (int)fastdiv(32u, p.magic_tc) * p.tmpl_chunks;
+                    for (int f = lane; f < n_chunks; f += 32) {
+                        dst[f] = s_tmpl[src];
+                        src += step;
+                        if (src >= p.tmpl_chunks) src -= p.tmpl_chunks;
+                    }
+                } else {
+                    if (hf) refill_stage();   // (the first half's image was requested at the top of the step)
+                    uint32_t ok = 0;
+                    while (!ok) {
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(tbar), "r"(tphase) : "memory");
+                    }
+                    tphase ^= 1u;
+                }
+                __syncwarp();
+                {
+                    const int total = nv_h * p.n_scan;
+                    for (int f = lane; f < total; f += 32) {
+                        const int el_l = (int)fastdiv((unsigned)f, p.magic_ns);
+                        const int el = e_lo + el_l;
+                        const uint32_t sc = s_scan[f - el_l * p.n_scan];
+                        const unsigned char *c = smap + el * span_stride + ((m0 + el * p.map_bytes) & 15) + (int)(sc & 0xffffu);
+                        const int o = c[0], st = c[2];
+                        if (o == 8 ? (st != 23) : (o != 2 && o != 10)) {
+                            const int code = (o == 8) ? kCodePot + min(st, 23) : min(o, 10);
+                            stage_record((2 * el_l) * C + (int)(sc >> 16), code);
+                            stage_record((2 * el_l + 1) * C + (int)(sc >> 16), code);
+                        }
+                    }
+                }
+                __syncwarp();
+                const bool mine = active && es >= e_lo && es < e_lo + nv_h;
+                if (mine) {
+                    const int el_l = es - e_lo, cell = ny * w + nx;
+                    stage_record((2 * el_l) * C + cell, code_v0);
+                    stage_record((2 * el_l + 1) * C + cell, ai ? code_v0 - 16 : code_v0 + 16);   // agent_1 is the viewer: "which" flips
+                }
+                __syncwarp();
+                {
+                    const unsigned urg_mask = __ballot_sync(0xffffffffu, mine && urg && ai == 0);
+                    if (urg_mask) {
+                        const int n_cells = 2 * nv_h * C;
+                        for (int g = lane; g < n_cells; g += 32) {
+                            const int slot = (int)fastdiv((unsigned)g, p.magic_C);
+                            if (s_ap[2 * (e_lo + (slot >> 1))]) stage[g * OC_OBS_CHANNELS + 25] = 1;
+                        }
+                    }
+                }
+                const size_t off_h = obs_off + (size_t)e_lo * 2 * env_bytes;
+                if (p.bulk_ok && nv_h == half) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_store(p.obs0 + off_h, smem_u32(stage), view_bytes);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    bulk_pending = true;
+                } else {
+                    __syncwarp();
+                    const int nb = 2 * nv_h * env_bytes;
+                    const unsigned short *h0 = reinterpret_cast<const unsigned short *>(stage);
+                    unsigned short *g0 = reinterpret_cast<unsigned short *>(p.obs0 + off_h);
+                    for (int k = lane; k < (nb >> 1); k += 32) g0[k] = h0[k];
+                    __syncwarp();
+                }
+            }
+        } else {
             const int urg = (p.max_steps - t_out) < 40;                                       // :311
             if (active) s_ap[lane] = (uint32_t)urg;
             // (4a) base image
@@ -470,8 +602,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.obs0 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
+                    bulk_store(p.obs0 + obs_off, smem_u32(stage), view_bytes);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 obs1_pending = true;      // issued after the state write-back below, which hides the engine's read
@@ -589,8 +720,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(p.obs1 + obs_off), "r"(smem_u32(stage)), "r"(view_bytes) : "memory");
+                bulk_store(p.obs1 + obs_off, smem_u32(stage), view_bytes);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             bulk_pending = true;
@@ -599,9 +729,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT) ? 7 
         if (MODE == MODE_ROLLOUT) {   // the next step starts from what this one produced (agent_dir is DIR_TO_VEC[dir_idx], :434-435)
             px = nx; py = ny; di = ndi; inv = ninv; t = t_out;
             dx = dir_x(ndi); dy = dir_y(ndi);
+            if (act_ring) {
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+                if (!last_ts && active) nact = (int)s_act[((ts + 1) & (ACT_RING - 1)) * 32 + lane];
+            }
             act = clampi(nact, 0, 5);
         }
       }   // ts
+        if (SPAN_BUFS == 1 && tile + tile_stride < p.n_tiles) {   // single span buffer: fetch the next tile once this one is stored
+            __syncwarp();
+            prefetch_spans(tile + tile_stride, 0);
+            nf = load_fields(tile + tile_stride);
+        }
     }
     if (STEPPING && p.ex.stats && blockIdx.x == 0 && tid == 0)   // every env stepped T times
         atomicAdd(reinterpret_cast<unsigned long long *>(p.ex.stats) + 6, (unsigned long long)p.N * (unsigned long long)T);

@@ -192,8 +192,13 @@ class Overcooked:
     def _check_out(self, out, batch):
         b = tuple(batch)
         img = b + (self.height, self.width, N_CHANNELS)
-        self._check(out["obs0"], "out['obs0']", torch.uint8, img)
-        self._check(out["obs1"], "out['obs1']", torch.uint8, img)
+        if out.get("obs_all") is not None:     # both views of an env side by side (oc_step_extras.obs_interleaved)
+            self._check(out["obs_all"], "out['obs_all']", torch.uint8, b + (2, self.height, self.width, N_CHANNELS))
+            if out.get("cells") is not None:
+                raise ValueError("out['obs_all'] cannot be combined with out['cells']")
+        else:
+            self._check(out["obs0"], "out['obs0']", torch.uint8, img)
+            self._check(out["obs1"], "out['obs1']", torch.uint8, img)
         for k in ("reward", "shaped0", "shaped1"):
             self._check(out[k], f"out['{k}']", torch.float32, b)
         self._check(out["done"], "out['done']", (torch.bool, torch.uint8), b)
@@ -279,12 +284,21 @@ class Overcooked:
             done = torch.empty(batch, dtype=torch.bool, device=self.device)
         else:
             self._check_out(out, batch)
-            obs0, obs1, reward, sh0, sh1, done = (out[k] for k in ("obs0", "obs1", "reward", "shaped0", "shaped1", "done"))
+            reward, sh0, sh1, done = (out[k] for k in ("reward", "shaped0", "shaped1", "done"))
+            if out.get("obs_all") is not None:
+                obs_all = out["obs_all"]
+                nb = len(batch)
+                obs0, obs1 = obs_all.select(nb, 0), obs_all.select(nb, 1)     # strided views of the one array
+            else:
+                obs0, obs1 = out["obs0"], out["obs1"]
         self._check_log(log, stats, batch)
         ex = None
         cells = out.get("cells") if out is not None else None
-        if log is not None or stats is not None or lazy is not None or cells is not None:
+        obs_all = out.get("obs_all") if out is not None else None
+        if log is not None or stats is not None or lazy is not None or cells is not None or obs_all is not None:
             e = _lib.StepExtras()
+            if obs_all is not None:
+                e.obs_interleaved = 1
             if cells is not None:
                 e.cells = cells.data_ptr()
             if lazy is not None:
@@ -298,9 +312,12 @@ class Overcooked:
             ex = C.byref(e)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.oc_step(self._handle, n, key_ptr, sp_in, a0.data_ptr(), a1.data_ptr(), rs,
-                                         sp_out, obs0.data_ptr(), obs1.data_ptr(), reward.data_ptr(), sh0.data_ptr(),
+                                         sp_out, obs0.data_ptr(), None if obs_all is not None else obs1.data_ptr(),
+                                         reward.data_ptr(), sh0.data_ptr(),
                                          sh1.data_ptr(), done.data_ptr(), ex, self._stream()), "oc_step")
         obs = {"agent_0": obs0, "agent_1": obs1}
+        if obs_all is not None:
+            obs["__all__"] = obs_all.view(tuple(batch) + (-1,))               # wrappers/baselines.py:196, no copy
         rewards = {"agent_0": reward, "agent_1": reward}                       # overcooked.py:124
         dones = {"agent_0": done, "agent_1": done, "__all__": done}            # :126
         infos = {"shaped_reward": {"agent_0": sh0, "agent_1": sh1}}            # :125, :133
@@ -314,7 +331,8 @@ class Overcooked:
           keys     uint32[T, N, 2] per-step per-env keys, or uint32[T, 2]: step t uses split(keys[t], N) derived in the kernel
                    (or a (keys[T, 2], num, first) tuple for one shard of a global batch of `num` envs)
           actions  {"agent_0": int32[T, N], "agent_1": int32[T, N]}, or a uint8[T, N] tensor (agent_0 | agent_1 << 4)
-          out      optional preallocated results: "obs" uint8[T, 2, N, h, w, 26] (the learners' layout: out["obs"][t].view(2N, -1)
+          out      optional preallocated results: "obs_all" uint8[T, N, 2, h, w, 26] (the VDN global state, both views of an env side
+                   by side), or "obs" uint8[T, 2, N, h, w, 26] (the learners' layout: out["obs"][t].view(2N, -1)
                    is batchify(obs) of step t) or "obs0"/"obs1" uint8[T, N, h, w, 26]; "reward"/"shaped0"/"shaped1" float32[T, N],
                    "done" bool[T, N]; or "results8" uint8[T, N] (packed) instead of the four; "cells" uint8[T, N, cell_stride]
           log      LogWrapper trackers [N, 2] (updated T times, in place); log["returned_episode"], if given, is [T, N, 2]
@@ -352,7 +370,15 @@ class Overcooked:
             io.act0, io.act1 = a0.data_ptr(), a1.data_ptr()
         out = dict(out) if out is not None else {}
         img = (h, w, N_CHANNELS)
-        if out.get("obs0") is not None:
+        obs_all = out.get("obs_all")
+        if obs_all is not None:       # uint8[T, N, 2, h, w, 26]: both views of an env side by side (oc_rollout_io.obs_interleaved)
+            self._check(obs_all, "out['obs_all']", torch.uint8, (T, n, 2) + img)
+            if out.get("cells") is not None:
+                raise ValueError("out['obs_all'] cannot be combined with out['cells']")
+            obs0, obs1 = obs_all[:, :, 0], obs_all[:, :, 1]
+            stride = 2 * n * h * w * N_CHANNELS
+            io.obs_interleaved = 1
+        elif out.get("obs0") is not None:
             obs0 = self._check(out["obs0"], "out['obs0']", torch.uint8, (T, n) + img)
             obs1 = self._check(out["obs1"], "out['obs1']", torch.uint8, (T, n) + img)
             if T > 1 and obs0.stride(0) != obs1.stride(0):
@@ -365,7 +391,7 @@ class Overcooked:
             self._check(obs, "out['obs']", torch.uint8, (T, 2, n) + img)
             obs0, obs1 = obs[:, 0], obs[:, 1]
             stride = 2 * n * h * w * N_CHANNELS
-        io.obs0, io.obs1, io.obs_step_stride = obs0.data_ptr(), obs1.data_ptr(), stride
+        io.obs0, io.obs1, io.obs_step_stride = obs0.data_ptr(), (None if obs_all is not None else obs1.data_ptr()), stride
         res8 = out.get("results8")
         reward = sh0 = sh1 = done = None
         if res8 is not None:
@@ -397,6 +423,8 @@ class Overcooked:
             _lib.check(self._lib.oc_rollout(self._handle, n, T, key_ptr, sp, C.byref(io), C.byref(e), self._stream()),
                        "oc_rollout")
         obs_d = {"agent_0": obs0, "agent_1": obs1}
+        if obs_all is not None:
+            obs_d["__all__"] = obs_all.view(T, n, -1)
         if res8 is not None:
             return obs_d, state, {"results8": res8}, {"results8": res8}, {"results8": res8}
         rewards = {"agent_0": reward, "agent_1": reward}
@@ -433,6 +461,18 @@ class Overcooked:
                                                   obs1.data_ptr(), cells.data_ptr() if cells is not None else None,
                                                   self._stream()), "oc_get_obs")
         return {"agent_0": obs0, "agent_1": obs1}
+
+    def get_obs_all(self, state, out=None):
+        """Both agents' observations as ONE uint8[..., 2, h, w, 26] array (`oc_get_obs_all`): `[..., 0]` / `[..., 1]` are
+        get_obs()["agent_0"] / ["agent_1"], and flattened per env it is the CTRolloutManager's obs["__all__"]."""
+        batch = tuple(state.time.shape)
+        n = int(np.prod(batch)) if batch else 1
+        shp = batch + (2, self.height, self.width, N_CHANNELS)
+        obs_all = torch.empty(shp, dtype=torch.uint8, device=self.device) if out is None else self._check(out, "out", torch.uint8, shp)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.oc_get_obs_all(self._handle, n, self._state_ptrs(state, batch), obs_all.data_ptr(),
+                                                self._stream()), "oc_get_obs_all")
+        return obs_all
 
     def empty_cells(self, n):
         """Buffer for the compact observations of `n` environments (see include/oc_b200.h, oc_step_extras.cells)."""

@@ -82,22 +82,31 @@ class CTRolloutManager(JaxMARLWrapper):
         inner = env
         while hasattr(inner, "_env"):
             inner = inner._env
+        self._inner = inner
         self._impl = "threefry_partitionable" if inner.prng_mode else "threefry_legacy"
 
-    def _global_state(self, obs):
-        return torch.cat([obs[a].reshape(self.batch_size, -1) for a in self.agents], dim=-1)
+    def _obs_from_all(self, obs_all):
+        """obs dict over ONE uint8[N, 2, h, w, 26] array written by the kernel: the per-agent observations are its [:, a]
+        slices and the global state (wrappers/baselines.py:196) is the same memory flattened per env -- no concatenation."""
+        return {"agent_0": obs_all[:, 0], "agent_1": obs_all[:, 1], "__all__": obs_all.view(self.batch_size, -1)}
 
     def batch_reset(self, key):
         from . import random as jr
-        obs, state = self._env.reset(jr.split(key, self.batch_size, impl=self._impl))
-        obs = dict(obs)
-        obs["__all__"] = self._global_state(obs)
-        return obs, state
+        _, state = self._env.reset(jr.split(key, self.batch_size, impl=self._impl))
+        inner_state = state.env_state if hasattr(state, "env_state") else state
+        return self._obs_from_all(self._inner.get_obs_all(inner_state)), state
 
     def batch_step(self, key, states, actions, **kw):
         from . import random as jr
-        obs, states, reward, done, infos = self._env.step(jr.LazySplit(key, self.batch_size), states, actions, **kw)
-        obs, reward = dict(obs), dict(reward)
-        obs["__all__"] = self._global_state(obs)
-        reward["__all__"] = reward[self.training_agents[0]]
+        inner = self._inner
+        out = dict(kw.pop("out", None) or {})
+        n, dev = self.batch_size, inner.device
+        if out.get("obs_all") is None:
+            out["obs_all"] = torch.empty((n, 2, inner.height, inner.width, 26), dtype=torch.uint8, device=dev)
+        for k, dt in (("reward", torch.float32), ("shaped0", torch.float32), ("shaped1", torch.float32), ("done", torch.bool)):
+            if out.get(k) is None:
+                out[k] = torch.empty((n,), dtype=dt, device=dev)
+        obs, states, reward, done, infos = self._env.step(jr.LazySplit(key, self.batch_size), states, actions, out=out, **kw)
+        reward = dict(reward)
+        reward["__all__"] = reward[self.training_agents[0]]                    # wrappers/baselines.py:197,229
         return obs, states, reward, done, infos

@@ -12,6 +12,8 @@ ap.add_argument("--layout", default="cramped_room")
 ap.add_argument("--sizes", default="16,256,4096,16384,65536,262144")
 ap.add_argument("--T", default="16")
 ap.add_argument("--packed", action="store_true")
+ap.add_argument("--packed-in", action="store_true", help="uint8 actions only")
+ap.add_argument("--packed-out", action="store_true", help="uint8 results only")
 ap.add_argument("--random-reset", action="store_true")
 ap.add_argument("--log", action="store_true")
 ap.add_argument("--min-ms", type=float, default=150.0)
@@ -30,12 +32,14 @@ for T in [int(x) for x in args.T.split(",")]:
         nbuf = max(2, min(8, int(300e6 // (2 * view * T)) + 1))      # rotate so that the obs written per cycle exceed L2
         obs = [torch.empty((T, 2, N, env.height, env.width, 26), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
         nact = 4
-        if args.packed:
+        if args.packed or args.packed_in:
             acts = [(torch.randint(0, 6, (T, N), device=dev) | (torch.randint(0, 6, (T, N), device=dev) << 4)).to(torch.uint8) for _ in range(nact)]
-            out = {"results8": torch.empty((T, N), dtype=torch.uint8, device=dev)}
         else:
             acts = [{"agent_0": torch.randint(0, 6, (T, N), dtype=torch.int32, device=dev),
                      "agent_1": torch.randint(0, 6, (T, N), dtype=torch.int32, device=dev)} for _ in range(nact)]
+        if args.packed or args.packed_out:
+            out = {"results8": torch.empty((T, N), dtype=torch.uint8, device=dev)}
+        else:
             out = {"reward": torch.empty((T, N), device=dev), "shaped0": torch.empty((T, N), device=dev),
                    "shaped1": torch.empty((T, N), device=dev), "done": torch.empty((T, N), dtype=torch.bool, device=dev)}
         keys = ocr.split_chain(ocr.PRNGKey(1), T)
@@ -62,7 +66,7 @@ for T in [int(x) for x in args.T.split(",")]:
             iters *= 2
         us = ms * 1e3 / (iters * T)
         line = {"kernel": "oc_rollout", "layout": args.layout, "N": N, "T": T, "us_per_step": round(us, 3), "env_steps_per_s": round(N / us * 1e6),
-                "frac_1277": round(B * N / (us * 1e-6) / PEAK, 4), "packed": args.packed, "log": args.log, "obs_bufs": nbuf}
+                "frac_1277": round(B * N / (us * 1e-6) / PEAK, 4), "packed": args.packed, "packed_in": args.packed_in, "packed_out": args.packed_out, "lib": os.path.basename(os.environ.get("OC_B200_LIB", "in-tree")), "log": args.log, "obs_bufs": nbuf}
         if args.single:
             slot = [{"obs0": obs[k % nbuf][t, 0], "obs1": obs[k % nbuf][t, 1], "reward": out.get("reward", torch.empty((T, N), device=dev))[t],
                      "shaped0": torch.empty(N, device=dev), "shaped1": torch.empty(N, device=dev), "done": torch.empty(N, dtype=torch.bool, device=dev)}

@@ -211,3 +211,60 @@ def test_rollout_full_size_properties():
     for f in ("agent_pos", "agent_dir", "agent_dir_idx", "agent_inv", "maze_map", "time", "terminal"):
         assert torch.equal(getattr(st, f), getattr(st_b, f)), f
     assert int(done["__all__"].sum()) > 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# both views of an env side by side (oc_step_extras.obs_interleaved): the CTRolloutManager's obs["__all__"] from the kernel
+
+@pytest.mark.parametrize("layout_name,N,random_reset", [
+    ("cramped_room", 64, False), ("cramped_room", 45, True), ("cramped_room", 3, False), ("forced_coord", 130, True),
+    ("counter_circuit", 97, True), ("easy_layout_padded", 77, True), ("bottleneck_large", 40, True), ("smallest_kitchen", 513, True),
+])
+def test_interleaved_observations_equal_the_two_views(layout_name, N, random_reset):
+    """oc_get_obs_all / oc_step with obs_interleaved / oc_rollout with obs_interleaved against the two-array form."""
+    ocb, ocr, orc, gh = _mods()
+    T = 14
+    env, ref, st, rst, rng, a, impl = _setup(layout_name, N, T, 31, random_reset=random_reset, max_steps=11)
+    st_b, st_c = st.clone(), st.clone()
+    o = env.get_obs(st)
+    oa = env.get_obs_all(st)
+    assert torch.equal(oa[:, 0], o["agent_0"]) and torch.equal(oa[:, 1], o["agent_1"]), "get_obs_all"
+    sk = rng.integers(0, 2**32, (T, N, 2), dtype=np.uint32)
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    h, w = env.height, env.width
+    for t in range(T):
+        out = {"obs_all": torch.zeros((N, 2, h, w, 26), dtype=torch.uint8, device="cuda"),
+               "reward": torch.zeros(N, device="cuda"), "shaped0": torch.zeros(N, device="cuda"), "shaped1": torch.zeros(N, device="cuda"),
+               "done": torch.zeros(N, dtype=torch.bool, device="cuda")}
+        at = {"agent_0": acts["agent_0"][t], "agent_1": acts["agent_1"][t]}
+        ob, st, rw, dn, inf = env.step(gh.keys_to_dev(sk[t]), st, at, donate=True, out=out)
+        ob2, st_b, rw2, dn2, inf2 = env.step(gh.keys_to_dev(sk[t]), st_b, at, donate=True)
+        assert torch.equal(ob["agent_0"], ob2["agent_0"]) and torch.equal(ob["agent_1"], ob2["agent_1"]), f"t={t}"
+        assert torch.equal(ob["__all__"], torch.cat([ob2["agent_0"].reshape(N, -1), ob2["agent_1"].reshape(N, -1)], 1)), f"t={t} __all__"
+        assert torch.equal(rw["agent_0"], rw2["agent_0"]) and torch.equal(dn["__all__"], dn2["__all__"])
+        (r0, r1), rr, s0, s1, dd = ref.step(sk[t], rst, a[t, :, 0], a[t, :, 1])
+        assert_same(ob["agent_0"].cpu().numpy(), r0, f"t={t} obs0 vs oracle")
+        assert_same(ob["agent_1"].cpu().numpy(), r1, f"t={t} obs1 vs oracle")
+    gh.compare_state(st, rst, "after the steps")
+    # the same T steps as one rollout writing uint8[T, N, 2, h, w, 26]
+    obs_all = torch.zeros((T, N, 2, h, w, 26), dtype=torch.uint8, device="cuda")
+    obr, _, rwr, dnr, infr = env.rollout(gh.keys_to_dev(sk), st_c, acts, out={"obs_all": obs_all})
+    obr2, _, _, _, _ = env.rollout(gh.keys_to_dev(sk), st_c.clone(), acts)      # (continues from st_c's end state: only shapes are used)
+    assert obr["__all__"].shape == (T, N, 2 * h * w * 26) and obr2["agent_0"].shape == (T, N, h, w, 26)
+    gh.compare_state(st_c, rst, "after the interleaved rollout")
+    assert torch.equal(obr["agent_0"][T - 1], ob["agent_0"]) and torch.equal(obr["agent_1"][T - 1], ob["agent_1"])
+
+
+def test_interleaved_rollout_every_step():
+    ocb, ocr, orc, gh = _mods()
+    N, T = 1000, 20
+    env, ref, st, rst, rng, a, impl = _setup("cramped_room", N, T, 77, random_reset=True, max_steps=9)
+    st_b = st.clone()
+    keys = ocr.split_chain(ocr.PRNGKey(5), T)
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs_all = torch.zeros((T, N, 2, env.height, env.width, 26), dtype=torch.uint8, device="cuda")
+    oa, _, ra, da, ia = env.rollout(keys, st, acts, out={"obs_all": obs_all})
+    ob, _, rb, db, ib = env.rollout(keys, st_b, acts)
+    assert torch.equal(oa["agent_0"], ob["agent_0"]) and torch.equal(oa["agent_1"], ob["agent_1"])
+    assert torch.equal(ra["agent_0"], rb["agent_0"]) and torch.equal(da["__all__"], db["__all__"])
+    assert torch.equal(st.maze_map, st_b.maze_map)
