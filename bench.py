@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--rollout-steps", type=int, default=16,
                     help="steps per launch: oc_rollout keeps the environments on chip for this many steps (the callers' lax.scan "
                          "over env.step with the actions given); 0 = one oc_step launch per step in a replayed CUDA graph")
-    ap.add_argument("--e2e-wire", default="reference", choices=["reference", "packed"],
+    ap.add_argument("--e2e-wire", default="packed", choices=["reference", "packed"],
                     help="host wire format of the e2e leg: the reference's dtypes (int32 actions, float32 results: 21 B per "
                          "env-step) or the packed one (2 B per env-step); the other one is reported next to it")
     ap.add_argument("--no-graph", action="store_true")
@@ -104,12 +104,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def profiled_traffic(layout_name):
-    """dram bytes per launch from the committed ncu --set full capture, if there is one for this workload."""
+def profiled_traffic(layout_name, envs=None, steps=None):
+    """dram bytes per launch from the committed ncu --set full capture, if there is one for this workload
+    (rollout launches are keyed by layout, envs per launch and steps per launch)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh)
-        return t.get(layout_name, {}).get("dram_bytes_per_launch")
+        key = layout_name if steps is None else f"{layout_name}_rollout_{envs}x{steps}"
+        return t.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -601,6 +603,21 @@ def run_ours(args):
         ms = ev0.elapsed_time(ev1)
         if stats is not None and world > 1:
             dist.all_reduce(stats)     # the rollout statistics: the only collective on this path
+    policy_us = None
+    if args.policy and args.policy_input == "cells":
+        # the policy kernel alone, on the compact observations the timed region left behind (its own roofline line below)
+        evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            for b in range(R):
+                net.act_cells(params, cells[b], subkeys[0, 0], out=pol_out[b])
+            evp0.record(stream)
+            reps_p = 25
+            for _ in range(reps_p):
+                for b in range(R):
+                    net.act_cells(params, cells[b], subkeys[0, 0], out=pol_out[b])
+            evp1.record(stream)
+        torch.cuda.synchronize()
+        policy_us = evp0.elapsed_time(evp1) * 1e3 / (reps_p * R)
     stats_win = None
     if not args.no_stats_window and not args.policy:
         stats_win = stats_window(args, env, dev, world, rank, N)
@@ -723,7 +740,7 @@ def run_ours(args):
         hw_ = h * w
         b_kernel = 52 * hw_ + 21 + (6 * hw_ + 82) / RO
         roofline.update({"kernel": "oc_env_kernel<MODE_ROLLOUT>", "env_steps_per_launch": N * RO, "steps_per_launch": RO,
-                         "avg_launch_us": step_s * 1e6 * RO, "traffic": None,
+                         "avg_launch_us": step_s * 1e6 * RO, "traffic": profiled_traffic(args.layout, N, RO),
                          "kernel_bytes_per_env_step": b_kernel, "achieved_kernel_bytes": b_kernel * N / step_s / 1e9,
                          "frac_kernel_bytes": b_kernel * N / step_s / 1e9 / peak})
     cpu = None
@@ -755,7 +772,20 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
     if args.policy:
         line["metric"] = METRIC + ", rollout step = actor-critic forward + sample + env step"
-        line["roofline"] = None       # two kernels per step; profiles/README.md has each kernel's own numbers
+        # two kernels per step.  The env kernel's HBM roofline is the default run's; the policy kernel is bound by instruction
+        # issue, not by HBM or the tensor pipe: warp-instructions per row (ncu, profiles/r01_ncu_policy_kernel.txt)
+        # x rows / kernel time against 4 issue slots per SM-cycle
+        line["roofline"] = None
+        if policy_us is not None:
+            WI_ROW = 317.0
+            f_sm = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+            slots = 148 * 4 * f_sm
+            ach = WI_ROW * 2 * N / (policy_us * 1e-6)
+            line["roofline"] = {"bound": "issue", "kernel": "oc_policy_kernel<tanh, compact source>", "achieved": ach / 1e12,
+                                "peak": slots / 1e12, "unit": "T warp-instr/s", "frac": ach / slots, "traffic": None,
+                                "warp_instructions_per_row": WI_ROW, "rows_per_launch": 2 * N, "avg_launch_us": policy_us,
+                                "note": "issue-slot bound: 148 SMs x 4 schedulers x SM clock; DRAM < 1 % and tensor pipe < 10 % busy "
+                                        "for this kernel (profiles/r01_ncu_policy_kernel.txt)"}
         line["config"]["actions"] = ("sampled on the device from the actor-critic MLP (architectures/mlp.py, random orthogonal "
                                      "init, fp16 tensor-core layer 2) evaluated on the previous step's observations")
         line["config"]["policy_rows_per_step"] = 2 * N

@@ -95,13 +95,48 @@ bool state_aligned(const oc_state &s) {
            aligned_to(s.goal_pos, 4) && aligned_to(s.pot_pos, 4) && aligned_to(s.task_id, 4);
 }
 
+// shared memory of a tile shape: the per-CTA copy plan and one warp's area (staging image, span buffer(s), urgency flags, mbarrier)
+int pf_bytes_of(const DevLayout &L, int e) { return ((e * (L.span_stride / 16) * 4) + 15) & ~15; }
+int warp_bytes_of(const DevLayout &L, int e, int span_bufs) {
+    return ((e * L.C * OC_OBS_CHANNELS + span_bufs * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15;
+}
+bool tile_size_ok(const DevLayout &L, int e) { return ((e * L.C * OC_OBS_CHANNELS) % 16) == 0; }   // bulk-copy size rule
+constexpr int kActRingBytes = 4 * 32 * 4;   // oc_kernels.cuh: ACT_RING slots of 32 lanes
+
+// MODE_ROLLOUT keeps a tile for T steps, so its best tile shape depends on the batch.  Measured on B200 (cramped_room, us per
+// step by envs per warp; profiles/r02_rollout_tile_shapes.txt):
+//     envs      16    1024   4096   8192  16384  32768  65536
+//     2        2.63   2.87   3.44   4.77   9.09   17.7   34.7      few environments: a step is one warp's latency chain, so
+//     4        2.82   3.09   4.77   3.88   5.26   9.91   19.2      small tiles on many warps and SMs win;
+//     8        3.41   3.74   3.84   5.94   6.01   7.17   15.0      once every SM has a full set of resident warps, 16-env tiles
+//     16       4.19   4.73   4.90   6.24   6.26   6.90   14.4      win (every lane busy in the step logic, half the per-tile work)
+// OC_B200_RO_EPW overrides (tuning).
+int rollout_epw(const oc_layout *lay, long long N, int cells_smem) {
+    const DevLayout &H = lay->host;
+    auto fits = [&](int e) {
+        return tile_size_ok(H, e) &&
+               lay->hdr_bytes + pf_bytes_of(H, e) + lay->warps * (warp_bytes_of(H, e, 1) + kActRingBytes + cells_smem * e) <= 227 * 1024;
+    };
+    if (const char *ev = std::getenv("OC_B200_RO_EPW")) {
+        const int v = std::atoi(ev);
+        if ((v == 2 || v == 4 || v == 8 || v == 16) && fits(v)) return v;
+    }
+    const long long per_sm = (N + lay->num_sms - 1) / lay->num_sms;     // environments per SM
+    const int want = per_sm <= 28 ? 2 : per_sm <= 112 ? 4 : 16;
+    for (int e = want; e <= 16; e <<= 1)
+        if (fits(e)) return e;
+    for (int e = want >> 1; e >= 2; e >>= 1)
+        if (fits(e)) return e;
+    return lay->epw;
+}
+
 template <int MODE>
 int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     const DevLayout &H = lay->host;
     kp.L = lay->dev;
     kp.tmpl_tile = lay->tmpl_tile;
-    kp.epw = lay->epw;
-    kp.warp_bytes = lay->warp_bytes;
+    const int epw = (MODE == MODE_ROLLOUT) ? rollout_epw(lay, kp.N, kp.cells ? lay->cell_stride : 0) : lay->epw;
+    kp.epw = epw;
     kp.h = H.h; kp.w = H.w; kp.C = H.C; kp.WP = H.WP; kp.map_bytes = H.map_bytes; kp.span_off = H.span_off;
     kp.span_len = H.span_len; kp.span_stride = H.span_stride; kp.n_pot = H.n_pot;
     kp.max_steps = H.max_steps; kp.random_reset = H.random_reset; kp.part = H.prng_mode;
@@ -110,39 +145,40 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.n_scan = H.n_scan; kp.tmpl_k = H.tmpl_k; kp.tmpl_chunks = H.tmpl_chunks; kp.tmpl_bytes = lay->tmpl_smem_bytes;
     kp.scan_bytes = (H.n_scan * 4 + 15) & ~15;
     kp.nch = H.span_stride / 16; kp.magic_nch = magic_of((unsigned)kp.nch);
-    kp.pf_bytes = lay->pf_bytes;
-    kp.pf_invariant = (((long long)lay->epw * H.map_bytes) % 16 == 0 && (long long)lay->epw * H.map_bytes + 32 < 65536) ? 1 : 0;
+    kp.pf_bytes = pf_bytes_of(H, epw);
+    kp.pf_invariant = (((long long)epw * H.map_bytes) % 16 == 0 && (long long)epw * H.map_bytes + 32 < 65536) ? 1 : 0;
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.cell_stride = lay->cell_stride; kp.cell_agents = lay->cell_agents;
-    kp.n_tiles = (kp.N + lay->epw - 1) / lay->epw;
+    kp.n_tiles = (kp.N + epw - 1) / epw;
     if (kp.n_tiles < 1) return OC_OK;
     const bool with_cells = kp.cells != nullptr;
     if (with_cells && !aligned16(kp.cells)) return OC_ERR_ALIGNMENT;
-    if (kp.interleaved && (with_cells || lay->epw < 2 || MODE == MODE_RESET)) return OC_ERR_INVALID_ARG;
+    if (kp.interleaved && (with_cells || epw < 2 || MODE == MODE_RESET)) return OC_ERR_INVALID_ARG;
     const int var = kp.interleaved ? VAR_ALL : (with_cells ? VAR_CELLS : VAR_PLAIN);
     void (*kern)(const KParams) = kp.interleaved ? oc_env_kernel<MODE, (MODE == MODE_RESET) ? VAR_PLAIN : VAR_ALL>
                                   : (with_cells ? oc_env_kernel<MODE, VAR_CELLS> : oc_env_kernel<MODE, VAR_PLAIN>);
     // the compact observations of a tile are staged per warp, behind the warp's regular shared-memory area
-    const int cells_smem = with_cells ? lay->epw * lay->cell_stride : 0;
+    const int cells_smem = with_cells ? epw * lay->cell_stride : 0;
     // MODE_ROLLOUT keeps one span buffer per warp instead of two (oc_kernels.cuh: SPAN_BUFS)
-    const int warp_bytes0 = lay->warp_bytes - (MODE == MODE_ROLLOUT ? lay->epw * H.span_stride : 0);
-    const int smem_bytes0 = lay->smem_bytes - lay->warps * (lay->warp_bytes - warp_bytes0) + lay->warps * cells_smem;
-    const int act_smem = (MODE == MODE_ROLLOUT) ? 4 * 32 * 4 : 0;   // oc_kernels.cuh: ACT_RING slots of 32 lanes
-    const int smem_bytes = smem_bytes0 + lay->warps * act_smem;
+    const int warp_bytes0 = warp_bytes_of(H, epw, MODE == MODE_ROLLOUT ? 1 : 2);
+    const int act_smem = (MODE == MODE_ROLLOUT) ? kActRingBytes : 0;
+    const int smem_bytes = lay->hdr_bytes + kp.pf_bytes + lay->warps * (warp_bytes0 + act_smem + cells_smem);
     if (smem_bytes > 227 * 1024) return OC_ERR_UNSUPPORTED_LAYOUT;
     kp.act_off = warp_bytes0;
     kp.cells_off = warp_bytes0 + act_smem;
     kp.warp_bytes = warp_bytes0 + act_smem + cells_smem;
-    if (lay->occ[MODE + var * NUM_MODES] == 0) {
+    const int le = epw == 16 ? 4 : epw == 8 ? 3 : epw == 4 ? 2 : epw == 2 ? 1 : 0;
+    int &occ = (MODE == MODE_ROLLOUT) ? lay->occ_ro[var][le] : lay->occ[MODE + var * NUM_MODES];
+    if (occ == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, smem_bytes) != cudaSuccess)
             return fail_cuda();
-        lay->occ[MODE + var * NUM_MODES] = nb < 1 ? 1 : nb;
+        occ = nb < 1 ? 1 : nb;
     }
     // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
-    const long long resident = (long long)lay->num_sms * lay->occ[MODE + var * NUM_MODES];
+    const long long resident = (long long)lay->num_sms * occ;
     const long long want = (kp.n_tiles + lay->warps - 1) / lay->warps;
     long long ctas = want;
     if (want > resident) {
@@ -349,6 +385,8 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->tmpl_smem_bytes = tmpl_smem;
     lay->warps = W;
     lay->smem_bytes = kHdrBytesHost0 + lay->pf_bytes + W * lay->warp_bytes;
+    lay->hdr_bytes = kHdrBytesHost0;
+    std::memset(lay->occ_ro, 0, sizeof(lay->occ_ro));
     lay->num_sms = prop.multiProcessorCount;
     lay->cell_agents = (L.n_scan + 1) & ~1;
     lay->cell_stride = (lay->cell_agents + 5 + 15) & ~15;
@@ -356,8 +394,9 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->device = device;
     {   // tile-sized static observation image
         const size_t eb = (size_t)C * OC_OBS_CHANNELS;
-        std::vector<unsigned char> img((size_t)epw * eb);
-        for (int k = 0; k < epw; ++k) std::memcpy(img.data() + (size_t)k * eb, L.obs_tmpl, eb);
+        const int copies = 16;      // the largest tile any launch uses (MODE_ROLLOUT picks its shape per launch)
+        std::vector<unsigned char> img((size_t)copies * eb);
+        for (int k = 0; k < copies; ++k) std::memcpy(img.data() + (size_t)k * eb, L.obs_tmpl, eb);
         lay->tmpl_tile = nullptr;
         if (cudaMalloc(&lay->tmpl_tile, img.size()) != cudaSuccess) { delete lay; return fail_cuda(); }
         if (cudaMemcpy(lay->tmpl_tile, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {

@@ -90,6 +90,8 @@ struct oc_layout {
     unsigned char *tmpl_tile;
     int num_sms;
     int cell_stride, cell_agents;   // compact observation: bytes per env, offset of the agent entries (oc_step_extras.cells)
-    mutable int occ[NUM_VARS * NUM_MODES];   // resident CTAs per SM of each kernel mode (filled on first launch)
+    int hdr_bytes;             // CTA-shared header of the kernels' shared memory (bitmaps, scan list, static image)
+    mutable int occ[NUM_VARS * NUM_MODES];
+    mutable int occ_ro[NUM_VARS][5];   // MODE_ROLLOUT picks its tile shape per launch: resident CTAs per SM by log2(envs per warp)   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
 

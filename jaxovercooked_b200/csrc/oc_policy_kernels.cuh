@@ -97,10 +97,19 @@ struct PParams {
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// OC_POLICY_EXACT_TANH=1 (build option): libdevice's tanhf (<= 2 ulp) instead of the hardware approximation (max relative
+// error 2^-11); DESIGN.md section 9 states what each reaches against the float32 oracle
+#ifndef OC_POLICY_EXACT_TANH
+#define OC_POLICY_EXACT_TANH 0
+#endif
 __device__ __forceinline__ float act_tanh(float x) {
+#if OC_POLICY_EXACT_TANH
+    return tanhf(x);
+#else
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 template <int ACT>
 __device__ __forceinline__ float activate(float x) {

@@ -3,8 +3,11 @@
 // get_obs` keep their signatures under jit / vmap / scan (see INTEGRATION.md section 1 and
 // jaxovercooked_b200/jax_ffi.py).
 //
-// STATUS: NOT BUILT AND NOT TESTED IN THIS IMAGE -- JAX (and with it xla/ffi/api/ffi.h) cannot be installed here.
-// __graft_entry__.build() compiles this file only when `import jax` succeeds:
+// STATUS: EXPERIMENTAL, NEVER RUN -- JAX (and with it xla/ffi/api/ffi.h) cannot be installed in this image.  What is checked
+// here: the file compiles against a stand-in of the FFI header (tests/c_abi/xla_ffi_stub) that static_asserts every handler's
+// parameter list against its binding, position by position (tests/test_abi_and_host.py).  Run-time behaviour under XLA
+// (buffer aliasing, command-buffer capture, PRED layout) is unverified.
+// __graft_entry__.build() compiles this file against the real header only when `import jax` succeeds:
 //   g++ -O2 -std=c++17 -shared -fPIC -I$(python -c "import jax; print(jax.ffi.include_dir())") -Iinclude
 //       -I/usr/local/cuda/include jaxovercooked_b200/csrc/xla_ffi_shim.cc -Ljaxovercooked_b200 -loc_b200
 //       -o jaxovercooked_b200/liboc_b200_ffi.so
@@ -80,6 +83,55 @@ ffi::Error StepImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> k
                            shaped1->typed_data(), reinterpret_cast<uint8_t *>(done->typed_data()),
                            /*extras=*/nullptr, stream);
     return to_error(rc, "oc_step");
+}
+
+// env.step(key, state, actions, reset_state): the caller-supplied state an environment restarts from
+// (multi_agent_env.py:47,55-59) instead of reset(key_reset).  The second State travels as eleven more operands.
+#define OC_RS_ARGS                                                                                                \
+    ffi::Buffer<ffi::U32> r_agent_pos, ffi::Buffer<ffi::S8> r_agent_dir, ffi::Buffer<ffi::S32> r_agent_dir_idx,   \
+        ffi::Buffer<ffi::S32> r_agent_inv, ffi::Buffer<ffi::U32> r_goal_pos, ffi::Buffer<ffi::U32> r_pot_pos,     \
+        ffi::Buffer<ffi::PRED> r_wall_map, ffi::Buffer<ffi::U8> r_maze_map, ffi::Buffer<ffi::S32> r_time,         \
+        ffi::Buffer<ffi::PRED> r_terminal, ffi::Buffer<ffi::S32> r_task_id
+ffi::Error StepResetStateImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> keys, OC_STATE_ARGS,
+                              ffi::Buffer<ffi::S32> act0, ffi::Buffer<ffi::S32> act1, OC_RS_ARGS, OC_STATE_RETS,
+                              ffi::ResultBuffer<ffi::U8> obs0, ffi::ResultBuffer<ffi::U8> obs1,
+                              ffi::ResultBuffer<ffi::F32> reward, ffi::ResultBuffer<ffi::F32> shaped0,
+                              ffi::ResultBuffer<ffi::F32> shaped1, ffi::ResultBuffer<ffi::PRED> done) {
+    const int64_t n = leading_count(keys);
+    const oc_state rs = {r_agent_pos.typed_data(), r_agent_dir.typed_data(), r_agent_dir_idx.typed_data(),
+                         r_agent_inv.typed_data(), r_goal_pos.typed_data(), r_pot_pos.typed_data(),
+                         reinterpret_cast<uint8_t *>(r_wall_map.typed_data()), r_maze_map.typed_data(), r_time.typed_data(),
+                         reinterpret_cast<uint8_t *>(r_terminal.typed_data()), r_task_id.typed_data()};
+    const int rc = oc_step(reinterpret_cast<const oc_layout *>(layout), n, keys.typed_data(), OC_IN_STATE,
+                           act0.typed_data(), act1.typed_data(), &rs, OC_OUT_STATE, obs0->typed_data(), obs1->typed_data(),
+                           reward->typed_data(), shaped0->typed_data(), shaped1->typed_data(),
+                           reinterpret_cast<uint8_t *>(done->typed_data()), /*extras=*/nullptr, stream);
+    return to_error(rc, "oc_step");
+}
+
+// T steps of the same batch in one custom call -- what `jax.lax.scan(_env_step, ..., length=T)` over `jax.vmap(env.step)` does
+// when the actions are given (baselines/unused/random_actions.py:197-225): keys u32[T,N,2], actions i32[T,N]; observations
+// u8[T,N,h,w,26] per agent, reward / shaped f32[T,N], done bool[T,N].  The State results are aliased onto the State operands.
+ffi::Error RolloutImpl(cudaStream_t stream, int64_t layout, ffi::Buffer<ffi::U32> keys, OC_STATE_ARGS,
+                       ffi::Buffer<ffi::S32> act0, ffi::Buffer<ffi::S32> act1, OC_STATE_RETS,
+                       ffi::ResultBuffer<ffi::U8> obs0, ffi::ResultBuffer<ffi::U8> obs1,
+                       ffi::ResultBuffer<ffi::F32> reward, ffi::ResultBuffer<ffi::F32> shaped0,
+                       ffi::ResultBuffer<ffi::F32> shaped1, ffi::ResultBuffer<ffi::PRED> done) {
+    const auto kd = keys.dimensions();                          // [T, N, 2]
+    if (kd.size() != 3) return ffi::Error::Internal("oc_rollout: keys must be u32[T, N, 2]");
+    const int64_t T = kd[0], n = kd[1];
+    const oc_state in = OC_IN_STATE, out = OC_OUT_STATE;
+    if (in.maze_map != out.maze_map)      // oc_rollout steps in place: the caller must alias the State (input_output_aliases)
+        return ffi::Error::Internal("oc_rollout: the State results must alias the State operands");
+    oc_rollout_io io = {};
+    io.act0 = act0.typed_data(); io.act1 = act1.typed_data();
+    io.obs0 = obs0->typed_data(); io.obs1 = obs1->typed_data();
+    io.obs_step_stride = (int64_t)(obs0->element_count() / (size_t)(T > 0 ? T : 1));
+    io.reward = reward->typed_data(); io.shaped0 = shaped0->typed_data(); io.shaped1 = shaped1->typed_data();
+    io.done = reinterpret_cast<uint8_t *>(done->typed_data());
+    const int rc = oc_rollout(reinterpret_cast<const oc_layout *>(layout), n, (int32_t)T, keys.typed_data(), out, &io,
+                              /*extras=*/nullptr, stream);
+    return to_error(rc, "oc_rollout");
 }
 
 // the same step that additionally returns the compact observations uint8[N, cell_stride] (oc_step_extras.cells), the input
@@ -161,6 +213,33 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(OcStep, StepImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()   // shaped agent_1
                                   .Ret<ffi::Buffer<ffi::PRED>>()  // done
 );
+
+#define OC_BIND_STEP_RETS()                                                                                       \
+    .Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::Buffer<ffi::F32>>()                         \
+        .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::PRED>>()
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcStepResetState, StepResetStateImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("layout")
+                                  .Arg<ffi::Buffer<ffi::U32>>()   // keys
+                                  OC_BIND_STATE_ARGS()
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_0 actions
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_1 actions
+                                  OC_BIND_STATE_ARGS()            // reset_state
+                                  OC_BIND_STATE_RETS()
+                                  OC_BIND_STEP_RETS());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(OcRollout, RolloutImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("layout")
+                                  .Arg<ffi::Buffer<ffi::U32>>()   // keys [T, N, 2]
+                                  OC_BIND_STATE_ARGS()
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_0 actions [T, N]
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // agent_1 actions [T, N]
+                                  OC_BIND_STATE_RETS()
+                                  OC_BIND_STEP_RETS());
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(OcStepCells, StepCellsImpl,
                               ffi::Ffi::Bind()

@@ -1,8 +1,9 @@
 """JAX side of the XLA FFI binding (csrc/xla_ffi_shim.cc): lets the REFERENCE's `Overcooked` keep its
 `reset / step / get_obs` signatures under `jax.jit / jax.vmap / lax.scan` while the work runs in liboc_b200.so.
 
-STATUS: importable only where JAX (>= 0.4.31, `jax.ffi`) is installed -- NOT in this image, so nothing here is
-exercised by the test-suite; it is the binding a maintainer of the reference would add.
+STATUS: EXPERIMENTAL, NEVER RUN.  Importable only where JAX (>= 0.4.31, `jax.ffi`) is installed -- NOT in this image, so
+nothing here is exercised by the test-suite beyond a compile check of the C++ side against a stand-in header; it is the
+binding a maintainer of the reference would add.
 
     import jax_marl
     from jaxovercooked_b200 import jax_ffi
@@ -33,8 +34,8 @@ def _register():
         raise _lib.OcError(f"{_FFI_LIB} is missing: build it with __graft_entry__.build() on a machine that has JAX")
     C.CDLL(_lib.LIB_PATH, mode=C.RTLD_GLOBAL)              # the shim links against liboc_b200.so
     shim = C.CDLL(_FFI_LIB)
-    for name, sym in (("oc_step", "OcStep"), ("oc_reset", "OcReset"), ("oc_get_obs", "OcGetObs"),
-                      ("oc_policy_act_cells", "OcPolicyActCells")):
+    for name, sym in (("oc_step", "OcStep"), ("oc_step_reset_state", "OcStepResetState"), ("oc_rollout", "OcRollout"),
+                      ("oc_reset", "OcReset"), ("oc_get_obs", "OcGetObs"), ("oc_policy_act_cells", "OcPolicyActCells")):
         jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(getattr(shim, sym)), platform="CUDA")
     _registered = True
 
@@ -98,14 +99,33 @@ def bind(env, donate_state=True):
         return {"agent_0": res[0], "agent_1": res[1]}
 
     def step(self, key, state, actions, reset_state=None):
-        if reset_state is not None:
-            raise NotImplementedError("reset_state is not forwarded through the FFI shim (no reference caller uses it)")
         lead = key.shape[:-1]
         outs = (_state_types(lead, G, P) + obs_t(lead) + [jax.ShapeDtypeStruct(lead, jnp.float32)] * 3 +
                 [jax.ShapeDtypeStruct(lead, jnp.bool_)])
         aliases = {1 + i: i for i in range(11)} if donate_state else {}
-        res = jax.ffi.ffi_call("oc_step", outs, vmap_method="broadcast_all", input_output_aliases=aliases)(
-            key, *[jnp.asarray(getattr(state, f)) for f in _STATE_FIELDS],
+        operands = [key] + [jnp.asarray(getattr(state, f)) for f in _STATE_FIELDS] + [
+            jnp.asarray(actions["agent_0"], jnp.int32), jnp.asarray(actions["agent_1"], jnp.int32)]
+        target = "oc_step"
+        if reset_state is not None:      # multi_agent_env.py:47,55-59: eleven more operands, same results
+            operands += [jnp.asarray(getattr(reset_state, f)) for f in _STATE_FIELDS]
+            target = "oc_step_reset_state"
+        res = jax.ffi.ffi_call(target, outs, vmap_method="broadcast_all", input_output_aliases=aliases)(
+            *operands, layout=np.int64(handle))
+        st = type(state)(**dict(zip(_STATE_FIELDS, res[:11])))
+        obs0, obs1, reward, sh0, sh1, done = res[11:]
+        return ({"agent_0": obs0, "agent_1": obs1}, st, {"agent_0": reward, "agent_1": reward},
+                {"agent_0": done, "agent_1": done, "__all__": done}, {"shaped_reward": {"agent_0": sh0, "agent_1": sh1}})
+
+    def rollout(self, keys, state, actions):
+        """T steps in one custom call (`oc_rollout`): keys u32[T, N, 2], actions {agent: i32[T, N]}; returns what
+        `jax.lax.scan` over `jax.vmap(env.step)` would stack: obs u8[T, N, h, w, 26] per agent, reward / shaped f32[T, N],
+        done bool[T, N], and the final State (always aliased onto `state`: the kernel steps in place)."""
+        T, n = keys.shape[0], keys.shape[1]
+        lead = (n,)
+        outs = (_state_types(lead, G, P) + [jax.ShapeDtypeStruct((T, n, h, w, 26), jnp.uint8)] * 2 +
+                [jax.ShapeDtypeStruct((T, n), jnp.float32)] * 3 + [jax.ShapeDtypeStruct((T, n), jnp.bool_)])
+        res = jax.ffi.ffi_call("oc_rollout", outs, input_output_aliases={1 + i: i for i in range(11)})(
+            keys, *[jnp.asarray(getattr(state, f)) for f in _STATE_FIELDS],
             jnp.asarray(actions["agent_0"], jnp.int32), jnp.asarray(actions["agent_1"], jnp.int32), layout=np.int64(handle))
         st = type(state)(**dict(zip(_STATE_FIELDS, res[:11])))
         obs0, obs1, reward, sh0, sh1, done = res[11:]
@@ -115,6 +135,7 @@ def bind(env, donate_state=True):
     env.reset = types.MethodType(reset, env)
     env.step = types.MethodType(step, env)
     env.get_obs = types.MethodType(get_obs, env)
+    env.rollout = types.MethodType(rollout, env)
     return env
 
 

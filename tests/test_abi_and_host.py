@@ -129,3 +129,22 @@ def test_public_header_is_plain_c():
                         "-fsyntax-only", f.name], capture_output=True, text=True)
     os.unlink(f.name)
     assert r.returncode == 0, r.stderr
+
+
+def test_xla_ffi_shim_compiles_against_the_stub():
+    """csrc/xla_ffi_shim.cc cannot meet the real xla/ffi/api/ffi.h here (no JAX in the image).  Compile-only check against a
+    stand-in header that static_asserts every handler's parameter list against its binding, position by position, and
+    type-checks every call into include/oc_b200.h; and every FFI target jax_ffi.py registers is a symbol the shim defines."""
+    import re
+    import subprocess
+    shim = os.path.join(ROOT, "jaxovercooked_b200", "csrc", "xla_ffi_shim.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "c_abi", "xla_ffi_stub"),
+                        "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    defined = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", open(shim).read()))
+    src = open(os.path.join(ROOT, "jaxovercooked_b200", "jax_ffi.py")).read()
+    registered = set(re.findall(r'\("oc_\w+", "(Oc\w+)"\)', src))
+    assert registered and registered <= defined, (registered, defined)
+    called = set(re.findall(r'ffi_call\(\s*"(oc_\w+)"', src)) | {"oc_step_reset_state"}
+    names = set(re.findall(r'\("(oc_\w+)", "Oc\w+"\)', src))
+    assert called <= names, (called, names)

@@ -46,15 +46,19 @@ def test_gpu_arm_prints_the_contract_line(extra):
         assert k in d, k
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "u8"
     assert "workload" in d["config"] and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-    assert d["steps"] == 64 and d["replays"] == 4 and d["requested_steps"] == 64
+    # one replayed graph = 2 x 16 steps (two oc_rollout launches; --policy / --streams use the one-launch-per-step graph: 2 x 8)
+    block = 32 if (not extra or extra == ["--log-wrapper"]) else 16
+    assert d["steps"] == 64 and d["replays"] == 64 // block and d["requested_steps"] == 64
     if "--policy" not in extra:
         w = d["stats_window"]
         assert w["stats_allreduced"][6] == 24 * 2048 and w["allreduce_equals_sum_of_shards"] and w["steps"] == 24
     if not extra:
         r = d["roofline"]
         assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-        assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 8 * 2048
-        assert d["e2e"]["value"] > 0 and d["e2e"]["value"] != d["value"]
+        assert r["kernel"] == "oc_env_kernel<MODE_ROLLOUT>" and r["steps_per_launch"] == 16 and 0 < r["frac_kernel_bytes"] < r["frac"]
+        e = d["e2e"]
+        assert d["cpu_baseline"]["kind"] == "port" and e["wire"] == "packed" and e["h2d_bytes_per_step"] == 2048 and e["d2h_bytes_per_step"] == 2048
+        assert e["value"] > 0 and e["value"] != d["value"] and e["value_reference_wire"] > 0
 
 
 @pytest.mark.gpu
@@ -64,7 +68,7 @@ def test_gpu_arm_time_floor():
                           "--no-cpu", "--min-ms", "60", "--stats-steps", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert d["timed_window_ms"] >= 55.0 and d["steps"] == 16 * d["replays"] and d["steps"] > 20
+    assert d["timed_window_ms"] >= 55.0 and d["steps"] == 32 * d["replays"] and d["steps"] > 20
     assert abs(d["ms_per_step"] * d["steps"] - d["timed_window_ms"]) < 1e-6 * d["timed_window_ms"] + 1e-9
     assert d["e2e"]["steps"] >= 2000
 

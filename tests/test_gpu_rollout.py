@@ -268,3 +268,24 @@ def test_interleaved_rollout_every_step():
     assert torch.equal(oa["agent_0"], ob["agent_0"]) and torch.equal(oa["agent_1"], ob["agent_1"])
     assert torch.equal(ra["agent_0"], rb["agent_0"]) and torch.equal(da["__all__"], db["__all__"])
     assert torch.equal(st.maze_map, st_b.maze_map)
+
+
+@pytest.mark.parametrize("epw", [2, 4, 8, 16])
+@pytest.mark.parametrize("layout_name", ["cramped_room", "counter_circuit", "easy_layout_padded"])
+def test_rollout_every_tile_shape(epw, layout_name, monkeypatch):
+    """oc_rollout picks its tile shape (envs per warp) from the batch size; force each shape (ragged batch, resets, urgency)."""
+    ocb, ocr, orc, gh = _mods()
+    monkeypatch.setenv("OC_B200_RO_EPW", str(epw))
+    N, T = 203, 18
+    env, ref, st, rst, rng, a, impl = _setup(layout_name, N, T, 40 + epw, random_reset=True, max_steps=12)
+    sk = rng.integers(0, 2**32, (T, N, 2), dtype=np.uint32)
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs, _, rew, done, info = env.rollout(gh.keys_to_dev(sk), st, acts)
+    o0, o1 = obs["agent_0"].cpu().numpy(), obs["agent_1"].cpu().numpy()
+    for t in range(T):
+        (r0, r1), rr, s0, s1, dd = ref.step(sk[t], rst, a[t, :, 0], a[t, :, 1])
+        assert_same(o0[t], r0, f"t={t} obs0")
+        assert_same(o1[t], r1, f"t={t} obs1")
+        assert_same(rew["agent_0"][t].cpu().numpy(), rr, f"t={t} reward")
+        assert_same(done["__all__"][t].cpu().numpy(), dd, f"t={t} done")
+    gh.compare_state(st, rst, "after the rollout")
