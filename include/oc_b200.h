@@ -299,6 +299,13 @@ int oc_policy_create(const oc_policy_desc *desc, oc_policy **out);
 int oc_policy_update(oc_policy *p, const oc_policy_desc *desc, void *stream);
 void oc_policy_destroy(oc_policy *p);
 
+/* Sharded draws.  After oc_policy_set_shard(p, first, global_count) the categorical draws of the forward calls use the noise
+ * the single-device program would use: for oc_policy_forward_cells, env i of a call is env first + i of global_count
+ * environments (rows first + i and global_count + first + i of the 2 * global_count actor rows); for oc_policy_forward,
+ * row m is row first + m of global_count rows.  A GPU that owns one shard of the env axis then samples exactly the
+ * actions a single device would sample for those environments.  global_count = 0 switches it off (the default). */
+int oc_policy_set_shard(oc_policy *p, int64_t first, int64_t global_count);
+
 /* logits[M, action_dim], value[M] for obs[M, obs_dim] (rows contiguous).  If `key` (DEVICE uint32[2]) is given,
  * action[m] = argmax_a(logits[m, a] + gumbel(key, (1, M, A))[0, m, a]) and log_prob[m] = log_softmax(logits[m])[action[m]]
  * are written too.  logits / value / action / log_prob may each be NULL. */

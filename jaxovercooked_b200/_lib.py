@@ -67,7 +67,7 @@ class PolicyDesc(C.Structure):
 EXPORTS = ("oc_version", "oc_status_string", "oc_layout_create", "oc_layout_destroy", "oc_layout_query",
            "oc_reset", "oc_step", "oc_rollout", "oc_rollout_host", "oc_step_host", "oc_host_stepper_create", "oc_host_stepper_step",
            "oc_host_stepper_wait", "oc_host_stepper_destroy", "oc_get_obs", "oc_get_obs_all", "oc_prng_split", "oc_prng_chain",
-           "oc_policy_create", "oc_policy_update", "oc_policy_destroy", "oc_policy_forward", "oc_policy_forward_cells", "oc_policy_sample",
+           "oc_policy_create", "oc_policy_update", "oc_policy_set_shard", "oc_policy_destroy", "oc_policy_forward", "oc_policy_forward_cells", "oc_policy_sample",
            "oc_layout_obs_template", "oc_get_obs_cells", "oc_layout_cell_tables")
 
 _lib = None
@@ -134,6 +134,8 @@ def load():
     lib.oc_policy_create.argtypes = [C.POINTER(PolicyDesc), C.POINTER(C.c_void_p)]
     lib.oc_policy_update.restype = C.c_int
     lib.oc_policy_update.argtypes = [C.c_void_p, C.POINTER(PolicyDesc), C.c_void_p]
+    lib.oc_policy_set_shard.restype = C.c_int
+    lib.oc_policy_set_shard.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     lib.oc_policy_destroy.restype = None
     lib.oc_policy_destroy.argtypes = [C.c_void_p]
     lib.oc_policy_forward.restype = C.c_int

@@ -150,6 +150,10 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.cell_stride = lay->cell_stride; kp.cell_agents = lay->cell_agents;
     kp.n_tiles = (kp.N + epw - 1) / epw;
+    {   // small batches (< 6 MB of observations per step) are latency-bound: plain stores instead of the copy engine
+        static const int force = [] { const char *e = std::getenv("OC_B200_PLAIN_OBS"); return e ? std::atoi(e) : -1; }();
+        kp.plain_obs = force >= 0 ? force : ((long long)kp.N * 2 * H.C * OC_OBS_CHANNELS <= 6ll * 1024 * 1024 ? 1 : 0);
+    }
     if (kp.n_tiles < 1) return OC_OK;
     const bool with_cells = kp.cells != nullptr;
     if (with_cells && !aligned16(kp.cells)) return OC_ERR_ALIGNMENT;

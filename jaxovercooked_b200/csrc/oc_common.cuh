@@ -55,6 +55,7 @@ struct KParams {
     int cell_stride, cell_agents, cells_off;   // cells_off: staging area inside the warp's shared memory (CELLS launches)
     int epw;        // environments per warp tile: 16, 8, 4 or 2
     int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
+    int plain_obs;  // small batch: full tiles leave through plain 16-byte stores instead (latency, not bandwidth, is the issue)
     int warp_bytes; // shared memory per warp
     // scalar copies of the layout, so the hot loop reads them from the constant bank
     int h, w, C, WP, map_bytes, span_off, span_len, span_stride, n_pot, max_steps, random_reset, part;

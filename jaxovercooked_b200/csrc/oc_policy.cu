@@ -62,6 +62,7 @@ struct oc_policy {
     __half *emb;
     uint8_t *scan_cells;
     mutable bool repacked;      // set by create / update, cleared by the next forward
+    long long shard_first, shard_global;   // oc_policy_set_shard (global == 0: off)
 };
 
 namespace {
@@ -177,6 +178,12 @@ int oc_policy_create(const oc_policy_desc *d, oc_policy **out) {
     return OC_OK;
 }
 
+int oc_policy_set_shard(oc_policy *p, int64_t first, int64_t global_count) {
+    if (!p || first < 0 || global_count < 0 || (global_count && first >= global_count)) return OC_ERR_INVALID_ARG;
+    p->shard_first = first; p->shard_global = global_count;
+    return OC_OK;
+}
+
 int oc_policy_update(oc_policy *p, const oc_policy_desc *d, void *stream) {
     if (!p || !d || d->obs_dim != p->K || d->action_dim != p->A) return OC_ERR_INVALID_ARG;
     return policy_pack(p, d, static_cast<cudaStream_t>(stream));
@@ -201,6 +208,8 @@ int oc_policy_forward(const oc_policy *p, int64_t M, const uint8_t *obs, float *
     k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
     k.rpt = rows_per_tile(M, p->num_sms);
     k.n_tiles = (int)((M + k.rpt - 1) / k.rpt);
+    k.noise_first = p->shard_global ? p->shard_first : 0; k.noise_global = p->shard_global ? p->shard_global : M;
+    if (k.noise_first + M > k.noise_global || k.noise_global * p->A > 0x7fffffffll) return OC_ERR_INVALID_ARG;
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;
     const int grid = k.n_tiles < p->num_sms ? k.n_tiles : p->num_sms;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -223,6 +232,8 @@ int oc_policy_forward_cells(const oc_policy *p, int64_t N, const uint8_t *cells,
     k.w1 = p->w1; k.w2img = p->w2img; k.small = p->small; k.tmpl = p->tmpl;
     k.M = M; k.N = N; k.K = p->K; k.A = p->A; k.part = p->part;
     k.nvar = p->nvar; k.gshift = p->gshift; k.tv_stride = p->tv_stride;
+    k.noise_first = p->shard_global ? p->shard_first : 0; k.noise_global = p->shard_global ? p->shard_global : N;
+    if (k.noise_first + N > k.noise_global || 2 * k.noise_global * p->A > 0x7fffffffll) return OC_ERR_INVALID_ARG;
     k.rpt = rows_per_tile(M, p->num_sms);                      // a tile holds rpt / 2 envs, both views
     k.n_tiles = (int)((N + k.rpt / 2 - 1) / (k.rpt / 2));
     k.logits = logits; k.value = value; k.log_prob = log_prob; k.key = key; k.action = action;

@@ -93,6 +93,9 @@ struct PParams {
     const uint8_t *scan_cells;  // [n_scan] cell index of every scan slot
     long long N;
     int cell_stride, cell_agents, n_scan, C;
+    // sharded draws (oc_policy_set_shard): local unit i (an env for the compact source, a row otherwise) is unit noise_first + i
+    // of noise_global units -- the gumbel noise is indexed as the single-device program over the whole batch would index it
+    long long noise_first, noise_global;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -655,6 +658,13 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
             row = view * p.N + env;
             live = row_l < p.rpt && env < p.N;
         }
+        // the row whose noise this row draws, and the size of the noise array, in the single-device program
+        long long nrow = p.noise_first + row, ncount = p.noise_global;
+        if (PL == 0) {
+            const int ept = p.rpt >> 1, view = row_l >= ept ? 1 : 0;
+            nrow = view * p.noise_global + p.noise_first + ((long long)tile * ept + (row_l - view * ept));
+            ncount = 2 * p.noise_global;
+        }
         const int A = p.A;
         float l[NA];
 #pragma unroll
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_
         if (p.key) {
             int arg;
             float lp;
-            sample_lanes<TPR>(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(p.M * A), live ? row : 0, A, s4, l, arg, lp);
+            sample_lanes<TPR>(p.part, __ldg(p.key), __ldg(p.key + 1), (int)(ncount * A), live ? nrow : 0, A, s4, l, arg, lp);
             if (live && s4 == 0) {
                 if (p.action) p.action[row] = arg;
                 if (p.log_prob) p.log_prob[row] = lp;

@@ -105,10 +105,12 @@ class ActorCritic:
         d.layout = layout
         return d
 
-    def bind(self, params, obs_template=None, env=None):
+    def bind(self, params, obs_template=None, env=None, shard=None):
         """Pack `params` for the kernels (done implicitly by apply/act).  `obs_template` (uint8, obs_dim bytes) lets
         layer 1 be evaluated relative to an observation most rows are close to; `env` (an `Overcooked`) uses the env's own
-        static image for that and additionally enables `act_cells` / `apply_cells` on the env's compact observations."""
+        static image for that and additionally enables `act_cells` / `apply_cells` on the env's compact observations.
+        `shard=(first, global_count)`: this process holds envs (act_cells) / rows (act) [first, first + n) of a global batch and
+        draws exactly the actions the single-device program would draw for them (`oc_policy_set_shard`)."""
         p = params["params"]
         obs_dim = int(p["Dense_0"]["kernel"].shape[0])
         tmpl = None
@@ -127,6 +129,8 @@ class ActorCritic:
         with torch.cuda.device(p["Dense_0"]["kernel"].device):
             torch.cuda.current_stream().synchronize()          # the parameters may still be being written
             _lib.check(self._lib.oc_policy_create(C.byref(d), C.byref(h)), "oc_policy_create")
+        if shard is not None:
+            _lib.check(self._lib.oc_policy_set_shard(h, int(shard[0]), int(shard[1])), "oc_policy_set_shard")
         self._bound[id(p)] = [h, self._versions(p), (p, tmpl, env), obs_dim]
         return self
 

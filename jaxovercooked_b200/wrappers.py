@@ -63,6 +63,25 @@ class LogWrapper(JaxMARLWrapper):
         return obs, new_state, reward, done, info
 
 
+    def rollout(self, keys, state, actions, *, out=None, stats=None):
+        """T LogWrapper steps in ONE launch (`env.rollout`, oc_rollout): the scan of `_env_step` over the wrapped env
+        (baselines/IPPO_CL.py:520-560) with the T steps' actions given.  `state` (LogEnvState) is updated IN PLACE; `info`
+        carries `returned_episode` per step (bool[T, N, 2]) and the trackers after the last step."""
+        n = int(state.env_state.time.shape[0])
+        T = int(keys.shape[0]) if not isinstance(keys, tuple) else int(keys[0].shape[0])
+        trackers = {f: getattr(state, f) for f in ("episode_returns", "episode_lengths", "returned_episode_returns",
+                                                    "returned_episode_lengths")}
+        returned_episode = torch.empty((T, n, self._env.num_agents), dtype=torch.bool, device=self._env.device)
+        log = dict(trackers, returned_episode=returned_episode)
+        obs, _, reward, done, info = self._env.rollout(keys, state.env_state, actions, out=out, log=log, stats=stats)
+        if self.replace_info:
+            info = {}
+        info["returned_episode_returns"] = state.returned_episode_returns
+        info["returned_episode_lengths"] = state.returned_episode_lengths
+        info["returned_episode"] = returned_episode
+        return obs, state, reward, done, info
+
+
 class CTRolloutManager(JaxMARLWrapper):
     """Rollout manager of the Q-learning baselines (reference: jax_marl/wrappers/baselines.py:153-249) for the way
     the VDN scripts use it -- `CTRolloutManager(LogWrapper(make(...)), batch_size=num_envs, preprocess_obs=False)`

@@ -445,3 +445,38 @@ def test_policy_rollout_sees_parameter_updates():
     ro.run()
     lo, vo = po.forward(params, ro.transition_obs()[0].cpu().numpy())
     np.testing.assert_allclose(ro.value[0].cpu().numpy(), vo + 2.0, atol=TOL * max(1.0, np.abs(vo).max() + 2.0))
+
+
+def test_sharded_draws_equal_the_single_device_draws():
+    """oc_policy_set_shard: a process that holds envs [first, first + n) of a global batch samples exactly the actions (and
+    log-probs) the single-device forward over the whole batch samples for them; logits / values do not depend on the shard."""
+    import jaxovercooked_b200 as ocb
+    from jaxovercooked_b200 import random as ocr
+    from jaxovercooked_b200.policy import ActorCritic
+    from oracle import policy_oracle as po
+    N = 1000
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"], random_reset=True)
+    cells = env.empty_cells(N)
+    env.reset(ocr.split(ocr.PRNGKey(5), N), cells=cells)
+    params = po.make_params(11, env.height * env.width * 26)
+    params["params"]["Dense_2"]["kernel"] = params["params"]["Dense_2"]["kernel"] * 30.0
+    key = ocr.PRNGKey(77)
+    full = ActorCritic(6)
+    P = full.params_from_numpy(params)
+    full.bind(P, env=env)
+    a_f, lp_f, v_f, lg_f = full.act_cells(P, cells, key, want_logits=True)
+    for first, n in ((0, 300), (300, 333), (633, 367)):
+        net = ActorCritic(6)
+        Ps = net.params_from_numpy(params)
+        net.bind(Ps, env=env, shard=(first, N))
+        a, lp, v, lg = net.act_cells(Ps, cells[first:first + n].contiguous(), key, want_logits=True)
+        rows = torch.cat([torch.arange(first, first + n), N + torch.arange(first, first + n)]).cuda()
+        assert torch.equal(lg, lg_f[rows]) and torch.equal(v, v_f[rows])
+        assert torch.equal(a, a_f[rows]) and torch.equal(lp, lp_f[rows])
+    # ... and without the shard information the same slice draws different noise
+    net = ActorCritic(6)
+    Ps = net.params_from_numpy(params)
+    net.bind(Ps, env=env)
+    a, _, _ = net.act_cells(Ps, cells[300:633].contiguous(), key)
+    rows = torch.cat([torch.arange(300, 633), N + torch.arange(300, 633)]).cuda()
+    assert not torch.equal(a, a_f[rows])

@@ -289,3 +289,24 @@ def test_rollout_every_tile_shape(epw, layout_name, monkeypatch):
         assert_same(rew["agent_0"][t].cpu().numpy(), rr, f"t={t} reward")
         assert_same(done["__all__"][t].cpu().numpy(), dd, f"t={t} done")
     gh.compare_state(st, rst, "after the rollout")
+
+
+def test_logwrapper_rollout_equals_logwrapper_steps():
+    ocb, ocr, orc, gh = _mods()
+    N, T = 500, 30
+    env, ref, st, rst, rng, a, impl = _setup("cramped_room", N, T, 61, random_reset=True, max_steps=8, time_offsets=False)
+    wenv = ocb.LogWrapper(env)
+    k0 = ocr.split(ocr.PRNGKey(9), N)
+    _, ls_a = wenv.reset(k0)
+    _, ls_b = wenv.reset(k0)
+    keys = ocr.split_chain(ocr.PRNGKey(10), T)
+    acts = {"agent_0": gh.to_dev(a[:, :, 0]), "agent_1": gh.to_dev(a[:, :, 1])}
+    obs, ls_a2, rew, done, info = wenv.rollout(keys, ls_a, acts)
+    assert ls_a2 is ls_a
+    for t in range(T):
+        ob, ls_b, rw, dn, inf = wenv.step(ocr.LazySplit(keys[t], N), ls_b, {"agent_0": acts["agent_0"][t], "agent_1": acts["agent_1"][t]}, donate=True)
+        assert torch.equal(ob["agent_0"], obs["agent_0"][t]) and torch.equal(dn["__all__"], done["__all__"][t])
+        assert torch.equal(inf["returned_episode"], info["returned_episode"][t])
+    for f in LOG_FIELDS:
+        assert torch.equal(getattr(ls_a, f), getattr(ls_b, f)), f
+    assert torch.equal(info["returned_episode_returns"], ls_b.returned_episode_returns) and float(ls_a.returned_episode_lengths.max()) == 8.0
