@@ -111,18 +111,22 @@ constexpr int kActRingBytes = 4 * 32 * 4;   // oc_kernels.cuh: ACT_RING slots of
 //     8        3.41   3.74   3.84   5.94   6.01   7.17   15.0      once every SM has a full set of resident warps, 16-env tiles
 //     16       4.19   4.73   4.90   6.24   6.26   6.90   14.4      win (every lane busy in the step logic, half the per-tile work)
 // OC_B200_RO_EPW overrides (tuning).
-int rollout_epw(const oc_layout *lay, long long N, int cells_smem) {
+int rollout_epw(const oc_layout *lay, long long N, int cells_smem, bool rollout) {
     const DevLayout &H = lay->host;
+    const int span_bufs = rollout ? 1 : 2;
     auto fits = [&](int e) {
-        return tile_size_ok(H, e) &&
-               lay->hdr_bytes + pf_bytes_of(H, e) + lay->warps * (warp_bytes_of(H, e, 1) + kActRingBytes + cells_smem * e) <= 227 * 1024;
+        return tile_size_ok(H, e) && lay->hdr_bytes + pf_bytes_of(H, e) +
+               lay->warps * (warp_bytes_of(H, e, span_bufs) + (rollout ? kActRingBytes : 0) + cells_smem * e) <= 227 * 1024;
     };
-    if (const char *ev = std::getenv("OC_B200_RO_EPW")) {
+    if (const char *ev = std::getenv(rollout ? "OC_B200_RO_EPW" : "OC_B200_STEP_EPW")) {
         const int v = std::atoi(ev);
         if ((v == 2 || v == 4 || v == 8 || v == 16) && fits(v)) return v;
     }
     const long long per_sm = (N + lay->num_sms - 1) / lay->num_sms;     // environments per SM
-    const int want = per_sm <= 28 ? 2 : per_sm <= 112 ? 4 : 16;
+    // one launch per step (oc_step / oc_get_obs / oc_reset): the layout's shape (8 envs per warp for cramped_room: 16 measured 8 %
+    // slower there) unless the batch is small, where the same latency argument as for rollouts holds
+    const int want = per_sm <= 28 ? 2 : per_sm <= 112 ? 4 : (rollout ? 16 : lay->epw);
+    if (!rollout && want >= lay->epw) return lay->epw;
     for (int e = want; e <= 16; e <<= 1)
         if (fits(e)) return e;
     for (int e = want >> 1; e >= 2; e >>= 1)
@@ -135,7 +139,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     const DevLayout &H = lay->host;
     kp.L = lay->dev;
     kp.tmpl_tile = lay->tmpl_tile;
-    const int epw = (MODE == MODE_ROLLOUT) ? rollout_epw(lay, kp.N, kp.cells ? lay->cell_stride : 0) : lay->epw;
+    const int epw = rollout_epw(lay, kp.N, kp.cells ? lay->cell_stride : 0, MODE == MODE_ROLLOUT);
     kp.epw = epw;
     kp.h = H.h; kp.w = H.w; kp.C = H.C; kp.WP = H.WP; kp.map_bytes = H.map_bytes; kp.span_off = H.span_off;
     kp.span_len = H.span_len; kp.span_stride = H.span_stride; kp.n_pot = H.n_pot;
@@ -150,10 +154,6 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.magic_ns = magic_of((unsigned)(H.n_scan > 0 ? H.n_scan : 1)); kp.magic_tc = magic_of((unsigned)H.tmpl_chunks);
     kp.cell_stride = lay->cell_stride; kp.cell_agents = lay->cell_agents;
     kp.n_tiles = (kp.N + epw - 1) / epw;
-    {   // small batches (< 6 MB of observations per step) are latency-bound: plain stores instead of the copy engine
-        static const int force = [] { const char *e = std::getenv("OC_B200_PLAIN_OBS"); return e ? std::atoi(e) : -1; }();
-        kp.plain_obs = force >= 0 ? force : ((long long)kp.N * 2 * H.C * OC_OBS_CHANNELS <= 6ll * 1024 * 1024 ? 1 : 0);
-    }
     if (kp.n_tiles < 1) return OC_OK;
     const bool with_cells = kp.cells != nullptr;
     if (with_cells && !aligned16(kp.cells)) return OC_ERR_ALIGNMENT;
@@ -172,7 +172,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.cells_off = warp_bytes0 + act_smem;
     kp.warp_bytes = warp_bytes0 + act_smem + cells_smem;
     const int le = epw == 16 ? 4 : epw == 8 ? 3 : epw == 4 ? 2 : epw == 2 ? 1 : 0;
-    int &occ = (MODE == MODE_ROLLOUT) ? lay->occ_ro[var][le] : lay->occ[MODE + var * NUM_MODES];
+    int &occ = lay->occ_ro[MODE][var][le];
     if (occ == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
@@ -394,7 +394,6 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     lay->num_sms = prop.multiProcessorCount;
     lay->cell_agents = (L.n_scan + 1) & ~1;
     lay->cell_stride = (lay->cell_agents + 5 + 15) & ~15;
-    for (int i = 0; i < NUM_VARS * NUM_MODES; ++i) lay->occ[i] = 0;
     lay->device = device;
     {   // tile-sized static observation image
         const size_t eb = (size_t)C * OC_OBS_CHANNELS;

@@ -55,7 +55,6 @@ struct KParams {
     int cell_stride, cell_agents, cells_off;   // cells_off: staging area inside the warp's shared memory (CELLS launches)
     int epw;        // environments per warp tile: 16, 8, 4 or 2
     int bulk_ok;    // obs base pointers are 16-byte aligned -> full tiles leave through the bulk-copy engine
-    int plain_obs;  // small batch: full tiles leave through plain 16-byte stores instead (latency, not bandwidth, is the issue)
     int warp_bytes; // shared memory per warp
     // scalar copies of the layout, so the hot loop reads them from the constant bank
     int h, w, C, WP, map_bytes, span_off, span_len, span_stride, n_pot, max_steps, random_reset, part;
@@ -92,7 +91,6 @@ struct oc_layout {
     int num_sms;
     int cell_stride, cell_agents;   // compact observation: bytes per env, offset of the agent entries (oc_step_extras.cells)
     int hdr_bytes;             // CTA-shared header of the kernels' shared memory (bitmaps, scan list, static image)
-    mutable int occ[NUM_VARS * NUM_MODES];
-    mutable int occ_ro[NUM_VARS][5];   // MODE_ROLLOUT picks its tile shape per launch: resident CTAs per SM by log2(envs per warp)   // resident CTAs per SM of each kernel mode (filled on first launch)
+    mutable int occ_ro[NUM_MODES][NUM_VARS][5];   // tile shapes are picked per launch: resident CTAs per SM by mode, variant, log2(envs per warp)   // resident CTAs per SM of each kernel mode (filled on first launch)
 };
 

@@ -598,20 +598,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT || VA
             code_v1 = kCodeAgent + (ai ? 0 : 16) + (ndi | (inv_code(ninv) << 2));
             my_cell = es * C + ny * w + nx;
             urg_lane = urg;
-            if ((MODE == MODE_ROLLOUT || MODE == MODE_OBS) && p.plain_obs && p.bulk_ok && n_valid == epw) {
-                // small batches: a step is one warp's latency chain, and the copy engine's read of the staging image sits on it
-                // twice per step; plain 16-byte stores are fire-and-forget (bandwidth is not the issue at these sizes)
-                __syncwarp();
-                const uint4 *h0 = reinterpret_cast<const uint4 *>(stage);
-                uint4 *g0 = reinterpret_cast<uint4 *>(p.obs0 + obs_off), *g1 = reinterpret_cast<uint4 *>(p.obs1 + obs_off);
-                const int nq = view_bytes >> 4;
-                for (int k = lane; k < nq; k += 32) g0[k] = h0[k];
-                __syncwarp();
-                if (active) stage_record(my_cell, code_v1);
-                if (urg && active) stage[my_cell * OC_OBS_CHANNELS + 25] = 1;
-                __syncwarp();
-                for (int k = lane; k < nq; k += 32) g1[k] = h0[k];
-            } else if (p.bulk_ok && n_valid == epw) {
+            if (p.bulk_ok && n_valid == epw) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {

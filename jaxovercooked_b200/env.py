@@ -656,9 +656,8 @@ class HostRollout:
         env._check_log(None if log is None else {k: v for k, v in log.items() if k != "returned_episode"}, stats, (n,))
         ex = self._ex
         ex.split_key = keys.data_ptr()
-        if log is not None:
-            for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths"):
-                setattr(ex, f, log[f].data_ptr())
+        for f in ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths"):
+            setattr(ex, f, log[f].data_ptr() if log is not None else None)      # (never keep a previous call's pointers)
         ex.stats = stats.data_ptr() if stats is not None else None
         self._keepalive = (keys, act, log, stats)
         with torch.cuda.device(env.device):

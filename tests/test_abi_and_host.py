@@ -148,3 +148,14 @@ def test_xla_ffi_shim_compiles_against_the_stub():
     called = set(re.findall(r'ffi_call\(\s*"(oc_\w+)"', src)) | {"oc_step_reset_state"}
     names = set(re.findall(r'\("(oc_\w+)", "Oc\w+"\)', src))
     assert called <= names, (called, names)
+
+
+def test_unpack_results8_numpy():
+    """The packed result byte of oc_rollout (reward/20 | class(shaped0) << 2 | class(shaped1) << 4 | done << 6), decoded on the host."""
+    import numpy as np
+    from jaxovercooked_b200.env import Overcooked
+    codes = np.array([0, 1, 2, 1 << 2, 2 << 2, 1 << 4, 2 << 4, 1 << 6, 2 | (2 << 2) | (1 << 4) | (1 << 6)], np.uint8)
+    r, s0, s1, d = Overcooked.unpack_results8(codes)
+    assert r.tolist() == [0, 20, 40, 0, 0, 0, 0, 0, 40] and r.dtype == np.float32
+    assert s0.tolist() == [0, 0, 0, 3, 5, 0, 0, 0, 5] and s1.tolist() == [0, 0, 0, 0, 0, 3, 5, 0, 3]
+    assert d.tolist() == [False] * 7 + [True, True]
