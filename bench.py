@@ -627,7 +627,8 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = n_global * K / (ms * 1e-3)
-    launches_per_block = ((2 if args.policy else 1) * BLOCK + 2) if not RO else 4   # rollout mode: 2 oc_rollout + 2 key-chain kernels   # our kernels: 16 steps (+ 16 policy forwards) + 2 key-chain kernels (the 2 RNG kernels are torch's)
+    # rollout mode: 2 oc_rollout + 2 key-chain kernels (+ 2 action pre-pack kernels for large int32 batches, oc_rollout_io)
+    launches_per_block = ((2 if args.policy else 1) * BLOCK + 2) if not RO else (4 + (2 if (N >= 32768 and h * w <= 64) else 0))   # our kernels: 16 steps (+ 16 policy forwards) + 2 key-chain kernels (the 2 RNG kernels are torch's)
     gpu_launches = (K // BLOCK) * launches_per_block + (stats_win["launches"] if stats_win else 0)
 
     # ---- e2e: the C-ABI call with HOST buffers (oc_step_host through env.host_stepper): every step copies that

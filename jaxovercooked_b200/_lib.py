@@ -52,7 +52,8 @@ class LayoutInfo(C.Structure):
 class RolloutIO(C.Structure):
     _fields_ = [("act0", C.c_void_p), ("act1", C.c_void_p), ("actions8", C.c_void_p), ("obs0", C.c_void_p),
                 ("obs1", C.c_void_p), ("obs_step_stride", C.c_int64), ("reward", C.c_void_p), ("shaped0", C.c_void_p),
-                ("shaped1", C.c_void_p), ("done", C.c_void_p), ("results8", C.c_void_p), ("obs_interleaved", C.c_int32)]
+                ("shaped1", C.c_void_p), ("done", C.c_void_p), ("results8", C.c_void_p), ("obs_interleaved", C.c_int32),
+                ("actions8_scratch", C.c_void_p)]
 
 
 WIRE_REFERENCE, WIRE_PACKED = 0, 1

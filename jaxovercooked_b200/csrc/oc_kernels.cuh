@@ -769,6 +769,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT || VA
 }
 
 
+// oc_rollout pre-pass: int32 actions of both agents -> one byte per env and step (the kernel's own clamp to 0..5 applied here)
+__global__ void oc_pack_actions_kernel(const int32_t *__restrict__ act0, const int32_t *__restrict__ act1, long long n,
+                                       uint8_t *__restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n && ((reinterpret_cast<uintptr_t>(act0 + i) | reinterpret_cast<uintptr_t>(act1 + i)) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(out + i) & 3) == 0) {
+            const int4 a = __ldg(reinterpret_cast<const int4 *>(act0 + i)), b = __ldg(reinterpret_cast<const int4 *>(act1 + i));
+            const uint32_t v = (uint32_t)(clampi(a.x, 0, 5) | (clampi(b.x, 0, 5) << 4)) |
+                               ((uint32_t)(clampi(a.y, 0, 5) | (clampi(b.y, 0, 5) << 4)) << 8) |
+                               ((uint32_t)(clampi(a.z, 0, 5) | (clampi(b.z, 0, 5) << 4)) << 16) |
+                               ((uint32_t)(clampi(a.w, 0, 5) | (clampi(b.w, 0, 5) << 4)) << 24);
+            *reinterpret_cast<uint32_t *>(out + i) = v;
+        } else {
+            for (long long j = i; j < n && j < i + 4; ++j)
+                out[j] = (uint8_t)(clampi(__ldg(act0 + j), 0, 5) | (clampi(__ldg(act1 + j), 0, 5) << 4));
+        }
+    }
+}
+
 // oc_reset pre-pass: constant ring + static State fields (the reset kernel then fills interior and dynamics)
 __global__ void oc_init_static_kernel(const DevLayout *__restrict__ L, long long N, oc_state st) {
     const long long stride = (long long)gridDim.x * blockDim.x;

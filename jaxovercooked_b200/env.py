@@ -368,6 +368,9 @@ class Overcooked:
             a0 = self._check(actions["agent_0"], "actions['agent_0']", torch.int32, (T, n))
             a1 = self._check(actions["agent_1"], "actions['agent_1']", torch.int32, (T, n))
             io.act0, io.act1 = a0.data_ptr(), a1.data_ptr()
+            if n >= 32768:     # large batches: the library packs the actions to one byte per env and step first (oc_rollout_io)
+                scratch8 = torch.empty((T, n), dtype=torch.uint8, device=dev)
+                io.actions8_scratch = scratch8.data_ptr()
         out = dict(out) if out is not None else {}
         img = (h, w, N_CHANNELS)
         obs_all = out.get("obs_all")
