@@ -134,7 +134,8 @@ typedef struct {
     int64_t map_bytes_per_env;       /* (h+8)*(w+8)*3 */
     int64_t obs_bytes_per_agent;     /* h*w*26        */
     int64_t algorithmic_bytes;       /* 58*h*w + 117 per env-step */
-    int32_t envs_per_warp, warps_per_cta, smem_bytes_per_cta;
+    int32_t envs_per_warp, warps_per_cta, smem_bytes_per_cta;   /* the layout's default tile shape (large one-step launches); oc_rollout
+                                                                    and small batches pick 2 / 4 / 8 / 16 envs per warp per launch */
     int32_t n_scan, cell_stride, cell_agents;   /* layout of oc_step_extras.cells */
 } oc_layout_info;
 

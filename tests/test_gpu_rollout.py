@@ -310,3 +310,40 @@ def test_logwrapper_rollout_equals_logwrapper_steps():
     for f in LOG_FIELDS:
         assert torch.equal(getattr(ls_a, f), getattr(ls_b, f)), f
     assert torch.equal(info["returned_episode_returns"], ls_b.returned_episode_returns) and float(ls_a.returned_episode_lengths.max()) == 8.0
+
+
+def _golden_rollout_cases():
+    from tests.helpers import golden_cases
+    return golden_cases()
+
+
+@pytest.mark.parametrize("case", _golden_rollout_cases())
+def test_rollout_matches_reference_golden(case):
+    """oc_rollout against the trajectories recorded from the reference's own source (no oracle in the loop): ALL steps of a
+    fixture in ONE launch -- up to a whole 400-step episode with the LogWrapper trackers carried in registers."""
+    from tests.helpers import DYN_FIELDS, load_golden
+    ocb, ocr, orc, gh = _mods()
+    g, meta, lay = load_golden(case)
+    if meta.get("crafted"):
+        pytest.skip("single-step crafted states are covered by test_gpu_parity")
+    env = ocb.make("overcooked", layout=lay, random_reset=meta["random_reset"], max_steps=meta["max_steps"], task_id=meta["task_id"],
+                   prng_impl="threefry_partitionable" if meta["partitionable"] else "threefry_legacy")
+    wenv = ocb.LogWrapper(env) if meta["log_wrapper"] else env
+    _, st = wenv.reset(gh.keys_to_dev(g["reset_keys"]))
+    T = g["actions"].shape[0]
+    acts = {"agent_0": gh.to_dev(g["actions"][:, :, 0]), "agent_1": gh.to_dev(g["actions"][:, :, 1])}
+    obs, st, rew, done, info = wenv.rollout(gh.keys_to_dev(g["step_keys"]), st, acts)
+    assert_same(obs["agent_0"].cpu().numpy(), g["s_obs0"], "obs0")
+    assert_same(obs["agent_1"].cpu().numpy(), g["s_obs1"], "obs1")
+    assert_same(rew["agent_0"].cpu().numpy(), g["s_reward"], "reward")
+    assert_same(info["shaped_reward"]["agent_0"].cpu().numpy(), g["s_shaped0"], "shaped0")
+    assert_same(info["shaped_reward"]["agent_1"].cpu().numpy(), g["s_shaped1"], "shaped1")
+    assert_same(done["__all__"].cpu().numpy(), g["s_done"], "done")
+    es = st.env_state if meta["log_wrapper"] else st
+    got = gh.state_to_numpy(es)
+    for f in DYN_FIELDS:
+        assert_same(got[f], g["s_" + f][T - 1], f"final {f}")
+    if meta["log_wrapper"]:
+        for f in LOG_FIELDS:
+            assert_same(getattr(st, f).cpu().numpy(), g["lw_" + f][T - 1], f"final log {f}")
+        assert_same(info["returned_episode"].cpu().numpy(), g["lw_returned_episode"], "returned_episode")
