@@ -54,9 +54,10 @@ def parse():
     ap.add_argument("--no-stats-window", action="store_true",
                     help="skip the LogWrapper-fused window whose int64[8] statistics are all-reduced over the ranks")
     ap.add_argument("--stats-steps", type=int, default=448)
-    ap.add_argument("--rollout-steps", type=int, default=16,
+    ap.add_argument("--rollout-steps", type=int, default=128,
                     help="steps per launch: oc_rollout keeps the environments on chip for this many steps (the callers' lax.scan "
-                         "over env.step with the actions given); 0 = one oc_step launch per step in a replayed CUDA graph")
+                         "over env.step with the actions given; default = the reference's own scan length, num_steps = 128, "
+                         "baselines/IPPO_CL.py:42,577); 0 = one oc_step launch per step in a replayed CUDA graph")
     ap.add_argument("--e2e-wire", default="packed", choices=["reference", "packed"],
                     help="host wire format of the e2e leg: the reference's dtypes (int32 actions, float32 results: 21 B per "
                          "env-step) or the packed one (2 B per env-step); the other one is reported next to it")
@@ -487,7 +488,7 @@ def run_ours(args):
         # learners' layout uint8[RO, 2, N, h, w, 26] (1.09 GB per half at 65,536 envs x 16 steps: far larger than L2)
         ro_act = torch.zeros((2, 2, RO, N), dtype=torch.int32, device=dev)
         ro_keys = torch.zeros((2, RO, 2), dtype=torch.uint32, device=dev)
-        n_ro_bufs = 2 if 2 * RO * 2 * N * h * w * 26 > 300e6 else 4
+        n_ro_bufs = 2 if RO * 2 * N * h * w * 26 > 150e6 else 4
         ro_out = [{"obs": torch.empty((RO, 2, N, h, w, 26), dtype=torch.uint8, device=dev),
                    "reward": torch.empty((RO, N), dtype=torch.float32, device=dev),
                    "shaped0": torch.empty((RO, N), dtype=torch.float32, device=dev),
@@ -585,7 +586,8 @@ def run_ours(args):
             est = torch.tensor([evw0.elapsed_time(evw1) / n_warm_blocks], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(est, op=dist.ReduceOp.MIN)
-            n_blocks = max(n_blocks, int(np.ceil(args.min_ms / max(float(est.item()), 1e-3))))
+            # (the warm-up estimate runs a little slow -- first replays -- so aim 20 % above the floor)
+            n_blocks = max(n_blocks, int(np.ceil(1.2 * args.min_ms / max(float(est.item()), 1e-3))))
         K = n_blocks * BLOCK
         if world > 1:
             dist.barrier()
@@ -641,6 +643,8 @@ def run_ours(args):
         # the RO steps' actions from pinned host memory, one launch, ONE device-to-host copy of the RO steps' rewards / shaped
         # rewards / dones into pinned host memory; the R env batches run on R streams.  Measured for both wire formats.
         Ke = max(2 * R * RO, args.e2e_steps if args.min_ms <= 0 else max(args.e2e_steps, 2000))
+        if args.min_ms > 0:          # the same time floor as the device-timed window
+            Ke = max(Ke, int(args.min_ms * 1e-3 / max(ms * 1e-3 / K, 1e-9)))
         n_ro = (Ke + RO - 1) // RO
         n_ro = ((n_ro + R - 1) // R) * R
         Ke = n_ro * RO
@@ -737,15 +741,19 @@ def run_ours(args):
                 "algorithmic_bytes_per_env_step": B_alg, "envs_per_launch": N, "avg_launch_us": step_s * 1e6,
                 "peak_source": peak_src}
     if RO:
-        # one launch = N envs x RO steps.  `achieved` follows SURVEY.md 8(d)'s per-env-step figure (state in + state out + both
-        # observations + keys/actions/results per step); the rollout kernel itself needs fewer bytes -- the state crosses HBM
-        # once per RO steps -- and that smaller figure is reported next to it
+        # one launch = N envs x RO steps.  SURVEY.md 8(d)'s per-env-step figure (1277 B for cramped_room) is per env.step CALL:
+        # state in + state out + both observations + keys/actions/results.  The rollout kernel moves the state once per RO steps,
+        # so the bytes IT must move per env-step are fewer: 52hw (observations) + 21 (actions in, results out) + (6hw + 82)/RO
+        # (state).  `achieved` / `frac` use that smaller, honest figure -- with SURVEY's figure the "fraction" would count bytes
+        # that are never moved (and exceeds 1 for long rollouts); it is reported next to it as *_survey_bytes.
         hw_ = h * w
         b_kernel = 52 * hw_ + 21 + (6 * hw_ + 82) / RO
+        ach_k = b_kernel * N / step_s / 1e9
         roofline.update({"kernel": "oc_env_kernel<MODE_ROLLOUT>", "env_steps_per_launch": N * RO, "steps_per_launch": RO,
                          "avg_launch_us": step_s * 1e6 * RO, "traffic": profiled_traffic(args.layout, N, RO),
-                         "kernel_bytes_per_env_step": b_kernel, "achieved_kernel_bytes": b_kernel * N / step_s / 1e9,
-                         "frac_kernel_bytes": b_kernel * N / step_s / 1e9 / peak})
+                         "algorithmic_bytes_per_env_step": b_kernel, "achieved": ach_k, "frac": ach_k / peak,
+                         "survey_8d_bytes_per_env_step": B_alg, "achieved_survey_bytes": achieved,
+                         "frac_survey_bytes": achieved / peak})
     cpu = None
     if world == 1 and not args.no_cpu and not args.policy:
         n_cpu = N          # the same batch the reference arm (`--impl reference`) steps

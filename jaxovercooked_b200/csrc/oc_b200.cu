@@ -140,6 +140,11 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     kp.L = lay->dev;
     kp.tmpl_tile = lay->tmpl_tile;
     const int epw = rollout_epw(lay, kp.N, kp.cells ? lay->cell_stride : 0, MODE == MODE_ROLLOUT);
+    int warps = lay->warps;      // warps per CTA (OC_B200_RO_WARPS: tuning knob for the rollout mode)
+    if (MODE == MODE_ROLLOUT) {
+        static const int w_env = [] { const char *e = std::getenv("OC_B200_RO_WARPS"); return e ? std::atoi(e) : 0; }();
+        if (w_env >= 1 && w_env <= lay->warps) warps = w_env;
+    }
     kp.epw = epw;
     kp.h = H.h; kp.w = H.w; kp.C = H.C; kp.WP = H.WP; kp.map_bytes = H.map_bytes; kp.span_off = H.span_off;
     kp.span_len = H.span_len; kp.span_stride = H.span_stride; kp.n_pot = H.n_pot;
@@ -166,7 +171,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     // MODE_ROLLOUT keeps one span buffer per warp instead of two (oc_kernels.cuh: SPAN_BUFS)
     const int warp_bytes0 = warp_bytes_of(H, epw, MODE == MODE_ROLLOUT ? 1 : 2);
     const int act_smem = (MODE == MODE_ROLLOUT) ? kActRingBytes : 0;
-    const int smem_bytes = lay->hdr_bytes + kp.pf_bytes + lay->warps * (warp_bytes0 + act_smem + cells_smem);
+    const int smem_bytes = lay->hdr_bytes + kp.pf_bytes + warps * (warp_bytes0 + act_smem + cells_smem);
     if (smem_bytes > 227 * 1024) return OC_ERR_UNSUPPORTED_LAYOUT;
     kp.act_off = warp_bytes0;
     kp.cells_off = warp_bytes0 + act_smem;
@@ -177,13 +182,13 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return fail_cuda();
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, lay->warps * 32, smem_bytes) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem_bytes) != cudaSuccess)
             return fail_cuda();
         occ = nb < 1 ? 1 : nb;
     }
     // persistent grid: every resident warp gets the same number of tiles (k), so there is no ragged last wave
     const long long resident = (long long)lay->num_sms * occ;
-    const long long want = (kp.n_tiles + lay->warps - 1) / lay->warps;
+    const long long want = (kp.n_tiles + warps - 1) / warps;
     long long ctas = want;
     if (want > resident) {
         const long long k = (want + resident - 1) / resident;
@@ -193,7 +198,7 @@ int launch_env(const oc_layout *lay, KParams &kp, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3((unsigned)lay->warps * 32);
+    cfg.blockDim = dim3((unsigned)warps * 32);
     cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -620,13 +620,12 @@ class HostRollout:
         self.first = int(first)
         n, T, dev = self.n, self.T, env.device
         self.stream = torch.cuda.Stream(dev) if stream is None else stream
+        self._actions = None               # pinned host action buffer, allocated on first use (callers may bring their own)
         if packed:
-            self.actions = torch.zeros((T, n), dtype=torch.uint8).pin_memory()
             self.results8 = torch.zeros((T, n), dtype=torch.uint8).pin_memory()
             self._results = self.results8
             self._scratch = torch.empty(2 * T * n + 16, dtype=torch.uint8, device=dev)
         else:
-            self.actions = torch.zeros((2, T, n), dtype=torch.int32).pin_memory()
             self._results = torch.zeros(13 * T * n, dtype=torch.uint8).pin_memory()
             tn = T * n
             self.reward = self._results[:4 * tn].view(torch.float32).view(T, n)
@@ -643,6 +642,14 @@ class HostRollout:
         self._stride = 2 * n * env.height * env.width * N_CHANNELS
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         self._call = env._lib.oc_rollout_host
+
+    @property
+    def actions(self):
+        """The pinned host tensor to fill with the T steps' actions (uint8[T, N] packed, int32[2, T, N] otherwise)."""
+        if self._actions is None:
+            shape, dt = ((self.T, self.n), torch.uint8) if self.packed else ((2, self.T, self.n), torch.int32)
+            self._actions = torch.zeros(shape, dtype=dt).pin_memory()
+        return self._actions
 
     def run(self, keys, actions=None, log=None, stats=None):
         """Enqueue T steps.  keys: uint32[T, 2] CUDA tensor (the T per-step subkeys); `actions`: a pinned host tensor to use

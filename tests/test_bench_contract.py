@@ -38,7 +38,7 @@ import pytest  # noqa: E402
 @pytest.mark.parametrize("extra", [[], ["--log-wrapper"], ["--policy"], ["--streams", "2"]])
 def test_gpu_arm_prints_the_contract_line(extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--envs", "2048", "--steps", "64", "--warmup", "3",
-                          "--cpu-seconds", "0.5", "--e2e-steps", "64", "--min-ms", "0", "--stats-steps", "24"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-seconds", "0.5", "--e2e-steps", "64", "--min-ms", "0", "--stats-steps", "24", "--rollout-steps", "16"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -55,7 +55,8 @@ def test_gpu_arm_prints_the_contract_line(extra):
     if not extra:
         r = d["roofline"]
         assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-        assert r["kernel"] == "oc_env_kernel<MODE_ROLLOUT>" and r["steps_per_launch"] == 16 and 0 < r["frac_kernel_bytes"] < r["frac"]
+        assert r["kernel"] == "oc_env_kernel<MODE_ROLLOUT>" and r["steps_per_launch"] == 16 and 0 < r["frac"] < r["frac_survey_bytes"]
+        assert abs(r["algorithmic_bytes_per_env_step"] - (52 * 20 + 21 + (6 * 20 + 82) / 16)) < 1e-9 and r["survey_8d_bytes_per_env_step"] == 1277
         e = d["e2e"]
         assert d["cpu_baseline"]["kind"] == "port" and e["wire"] == "packed" and e["h2d_bytes_per_step"] == 2048 and e["d2h_bytes_per_step"] == 2048
         assert e["value"] > 0 and e["value"] != d["value"] and e["value_reference_wire"] > 0
@@ -65,7 +66,7 @@ def test_gpu_arm_prints_the_contract_line(extra):
 def test_gpu_arm_time_floor():
     """Whatever --steps says, the device-timed window is at least --min-ms long and the end-to-end leg at least 2,000 steps."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--envs", "4096", "--steps", "20", "--warmup", "3",
-                          "--no-cpu", "--min-ms", "60", "--stats-steps", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--no-cpu", "--min-ms", "60", "--stats-steps", "8", "--rollout-steps", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["timed_window_ms"] >= 55.0 and d["steps"] == 32 * d["replays"] and d["steps"] > 20
