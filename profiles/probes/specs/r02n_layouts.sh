@@ -19,6 +19,6 @@ import json
 for l in open("gpurun_out/r02n_layouts.jsonl"):
     if not l.startswith("{"): continue
     d = json.loads(l); r = d.get("roofline") or {}
-    print(f"{d['config']['workload'][:70]:70s} lw={d['config'].get('log_wrapper')} {d['value']/1e9:7.3f} G  {d['ms_per_step']*1e3:7.2f} us  frac {r.get('frac', 0):.3f}  kfrac {r.get('frac_kernel_bytes', 0):.3f}")
+    print(f"{d['config']['workload'][:70]:70s} lw={d['config'].get('log_wrapper')} {d['value']/1e9:7.3f} G  {d['ms_per_step']*1e3:7.2f} us  frac {r.get('frac', 0):.3f}  survey-bytes frac {r.get("frac_survey_bytes", 0):.3f}")
 PY
 tail -3 gpurun_out/r02n.err
