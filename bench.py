@@ -645,16 +645,22 @@ def run_ours(args):
         Ke = max(2 * R * RO, args.e2e_steps if args.min_ms <= 0 else max(args.e2e_steps, 2000))
         if args.min_ms > 0:          # the same time floor as the device-timed window
             Ke = max(Ke, int(args.min_ms * 1e-3 / max(ms * 1e-3 / K, 1e-9)))
-        n_ro = (Ke + RO - 1) // RO
-        n_ro = ((n_ro + R - 1) // R) * R
-        Ke = n_ro * RO
+        # every concurrently stepping batch writes its OWN trajectory buffer: as many batches as fit next to the two buffers of
+        # the device-timed leg (all 8 for the default workload; fewer for layouts whose 128-step trajectories are tens of GB)
         torch.cuda.synchronize()
-        e_keys = ocr.split_chain(rngs[1 % R], (n_ro + 2 * R) * RO).view(n_ro + 2 * R, RO, 2)
+        buf_bytes = RO * 2 * N * h * w * 26
+        free_b = torch.cuda.mem_get_info(dev)[0]
+        Re = int(max(2, min(R, 2 + (0.85 * free_b) // buf_bytes)))
+        e_obs = [ro_out[i]["obs"] for i in range(min(2, n_ro_bufs))]
+        e_obs += [torch.empty_like(e_obs[0]) for _ in range(Re - len(e_obs))]
+        n_ro = (Ke + RO - 1) // RO
+        n_ro = ((n_ro + Re - 1) // Re) * Re
+        Ke = n_ro * RO
+        e_keys = ocr.split_chain(rngs[1 % R], (n_ro + 2 * Re) * RO).view(n_ro + 2 * Re, RO, 2)
         res_e2e = {}
         for wire in ("reference", "packed"):
             packed = wire == "packed"
-            # the trajectory buffers of the device-timed leg are reused (each HostRollout writes a [RO, 2, N, ...] buffer)
-            hrs = [ocb.HostRollout(env, states[b], RO, n_global, first, packed=packed, obs=ro_out[b % n_ro_bufs]["obs"]) for b in range(R)]
+            hrs = [ocb.HostRollout(env, states[b], RO, n_global, first, packed=packed, obs=e_obs[b]) for b in range(Re)]
             if packed:
                 h_pool = [(torch.randint(0, 6, (RO, N)) | (torch.randint(0, 6, (RO, N)) << 4)).to(torch.uint8).pin_memory() for _ in range(4)]
             else:
@@ -663,17 +669,17 @@ def run_ours(args):
 
             def e2e_run(i0, n):
                 for i in range(i0, i0 + n):
-                    hr = hrs[i % R]
+                    hr = hrs[i % Re]
                     hr.wait()                                    # this batch's previous results are on the host
                     hr.run(e_keys[i], h_pool[i % 4])
 
-            e2e_run(0, 2 * R)
+            e2e_run(0, 2 * Re)
             for hr in hrs:
                 hr.wait()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            e2e_run(2 * R, n_ro)
+            e2e_run(2 * Re, n_ro)
             for hr in hrs:
                 hr.wait()
             dt = time.perf_counter() - t0
@@ -694,7 +700,7 @@ def run_ours(args):
                "note": f"oc_rollout_host (C ABI, host buffers) via env.HostRollout: per {RO} steps of a batch one copy of the "
                        "actions from pinned host memory in, one launch, one copy of rewards+shaped+dones to pinned host memory "
                        "out (those bytes are counted per step); observations stay on the device for the learner, as in the "
-                       f"reference; {R} env batches pipelined on {R} streams"}
+                       f"reference; {Re} env batches pipelined on {Re} streams, each with its own trajectory buffer"}
     elif not args.log_wrapper and not args.policy and args.e2e_steps > 0:
         Ke = max(2 * R, args.e2e_steps if args.min_ms <= 0 else max(args.e2e_steps, 2000))
         torch.cuda.synchronize()

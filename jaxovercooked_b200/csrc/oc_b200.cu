@@ -356,7 +356,9 @@ int oc_layout_create(const oc_layout_desc *d, oc_layout **out) {
     // 16-byte size rule of the bulk copy (epw * C * 26 must be a multiple of 16); OC_B200_EPW overrides (tuning)
     const int smem_cap = 227 * 1024;
     auto pf_bytes_for = [&](int e) { return ((e * (L.span_stride / 16) * 4) + 15) & ~15; };
-    const int tmpl_smem = (L.tmpl_chunks * 16 <= 4096) ? L.tmpl_chunks * 16 : 0;
+    // static image kept in shared memory (copied by the lanes) up to this size; larger ones are pulled per tile by the copy engine
+    static const int tmpl_smem_max = [] { const char *e = std::getenv("OC_B200_TMPL_SMEM_MAX"); return e ? std::atoi(e) : 4096; }();
+    const int tmpl_smem = (L.tmpl_chunks * 16 <= tmpl_smem_max) ? L.tmpl_chunks * 16 : 0;
     const int kHdrBytesHost0 = kHdrFixed + ((L.n_scan * 4 + 15) & ~15) + tmpl_smem;
     auto warp_bytes_for = [&](int e) { return ((e * C * OC_OBS_CHANNELS + 2 * e * L.span_stride + 2 * e * 4 + 16) + 15) & ~15; };
     auto size_ok = [&](int e) { return ((e * C * OC_OBS_CHANNELS) % 16) == 0; };
