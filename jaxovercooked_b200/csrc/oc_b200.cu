@@ -123,6 +123,27 @@ int rollout_epw(const oc_layout *lay, long long N, int cells_smem, bool rollout)
         if ((v == 2 || v == 4 || v == 8 || v == 16) && fits(v)) return v;
     }
     const long long per_sm = (N + lay->num_sms - 1) / lay->num_sms;     // environments per SM
+    if (rollout && per_sm > 112) {
+        // large batch: the largest tile that still leaves enough resident warps per SM (shared memory decides).  Measured at
+        // 65,536 envs (us per step, 16 / 8 / 4 envs per warp; gpurun_out/r03f.txt): 6x6 28.2 / 24.6 / 24.9, 5x9 29.8 / 32.9 / 30.0,
+        // 7x9 56.3 / 43.7 / -, 8x10 76.9 / 50.1 / 55.8, 10x10 70.9 / 63.7 / 67.5, 9x11 83.0 / 65.3 / -: 8 resident warps are
+        // enough when the static image arrives through the copy engine, 12 are wanted when the lanes copy it
+        auto res_warps = [&](int e) {
+            const int cta = lay->hdr_bytes + pf_bytes_of(H, e) + lay->warps * (warp_bytes_of(H, e, 1) + kActRingBytes + cells_smem * e) + 1024;
+            int ctas = (227 * 1024) / cta;
+            if (ctas > 7) ctas = 7;                 // 72 registers x 128 threads
+            return ctas * lay->warps;
+        };
+        const int need = lay->tmpl_smem_bytes ? 12 : 8;
+        for (int e = 16; e >= 8; e >>= 1)
+            if (fits(e) && res_warps(e) >= need) return e;
+        for (int e = 16; e >= 8; e >>= 1)
+            if (fits(e) && res_warps(e) >= 8) return e;
+        int best_e = 0, best_w = 0;
+        for (int e = 16; e >= 2; e >>= 1)
+            if (fits(e) && res_warps(e) > best_w) { best_w = res_warps(e); best_e = e; }
+        if (best_e) return best_e;
+    }
     // one launch per step (oc_step / oc_get_obs / oc_reset): the layout's shape (8 envs per warp for cramped_room: 16 measured 8 %
     // slower there) unless the batch is small, where the same latency argument as for rollouts holds
     const int want = per_sm <= 28 ? 2 : per_sm <= 112 ? 4 : (rollout ? 16 : lay->epw);
