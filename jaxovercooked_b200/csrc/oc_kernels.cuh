@@ -7,9 +7,6 @@
 #ifndef OC_OBS_EVICT_FIRST
 #define OC_OBS_EVICT_FIRST 0
 #endif
-#ifndef OC_ACT_PREFETCH
-#define OC_ACT_PREFETCH 0
-#endif
 #ifndef OC_ROLLOUT_MIN_CTAS
 #define OC_ROLLOUT_MIN_CTAS 7   // resident CTAs per SM the rollout instantiation is compiled for (72 registers)
 #endif
@@ -199,24 +196,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (MODE == MODE_ROLLOUT || VA
     int buf = 0;
     Fields nf;
     if (tile < p.n_tiles) { prefetch_spans(tile, 0); nf = load_fields(tile); }
-#if OC_ACT_PREFETCH
-    // MODE_ROLLOUT, int32 actions: pull the action rows of ALL this warp's tiles and steps into L2 now, in one burst at the start of
-    // the launch, instead of one isolated DRAM read per tile and step in the middle of the observation write stream
-    if (MODE == MODE_ROLLOUT && !p.act8) {
-        for (long long tl = tile; tl < p.n_tiles; tl += tile_stride)
-            for (int t0 = 0; t0 < T; t0 += 16) {
-                const int tsp = t0 + (lane >> 1);
-                if (tsp < T) {
-                    const int32_t *a = ((lane & 1) ? p.act1 : p.act0) + (long long)tsp * p.N + tl * epw;
-#if OC_ACT_PREFETCH == 2
-                    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(a));
-#else
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
-#endif
-                }
-            }
-    }
-#endif
 
     for (; tile < p.n_tiles; tile += tile_stride, buf ^= (SPAN_BUFS - 1)) {
         const long long env0 = tile * epw;

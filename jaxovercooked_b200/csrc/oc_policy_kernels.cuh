@@ -40,7 +40,10 @@ constexpr int kHid = OC_POLICY_HIDDEN;        // 128
 constexpr int kHid2 = 2 * kHid;               // actor | critic
 constexpr int kTileM = 128;
 constexpr int kObsWarps = 16;                 // warps per CTA when rows are uint8 observations (register-hungry scan)
-constexpr int kCellWarps = 32;                // ... and when rows are compact observations (more warps hide the gather latency)
+#ifndef OC_POLICY_CELL_WARPS
+#define OC_POLICY_CELL_WARPS 32               // tuning: 16 leaves half of the SM's registers to a concurrently running env kernel
+#endif
+constexpr int kCellWarps = OC_POLICY_CELL_WARPS;   // ... and when rows are compact observations (more warps hide the gather latency)
 constexpr int kListCap = 512;                 // (k, delta) entries per warp between two flushes
 constexpr int kListWords = kListCap + 8;      // + padding to a multiple of 8 entries
 constexpr int kNetBytes = kTileM * kHid * 2;  // one fp16 128x128 operand image: 32 KB = 2 swizzle atoms of 16 KB
@@ -303,7 +306,7 @@ __device__ __forceinline__ void load_cells(const PParams &p, long long tile, int
 // PL > 0: rows are uint8 observations, PL 16-byte pieces per lane and row.  PL == 0: rows come from the env kernel's
 // compact observations (cells) and layer 1 is a sum of precomputed (view, cell, code) embeddings.
 template <int ACT, int PL>
-__global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, 1) oc_policy_kernel(const PParams p) {
+__global__ void __launch_bounds__((PL > 0 ? kObsWarps : kCellWarps) * 32, (PL == 0 && kCellWarps == 16) ? 2 : 1) oc_policy_kernel(const PParams p) {
     constexpr int PLA = PL > 0 ? PL : 1;
     constexpr int NW = PL > 0 ? kObsWarps : kCellWarps;     // warps per CTA
     constexpr int kPolThreads = NW * 32;
