@@ -90,6 +90,14 @@ def workload_name(args, lay):
             f"random_reset={bool(args.random_reset)}")
 
 
+def workload_config(args, lay, world):
+    """The `config` object: the workload only -- identical in our arm and in the reference arm (how each arm runs it is in `run`)."""
+    return {"workload": workload_name(args, lay), "layout": args.layout, "padded_cl": bool(args.padded_cl),
+            "grid": [int(lay["height"]), int(lay["width"])], "envs_per_gpu": args.envs, "global_envs": args.envs * world,
+            "max_steps": args.max_steps, "random_reset": bool(args.random_reset), "actions": "i.i.d. uniform {0..5}",
+            "log_wrapper": bool(args.log_wrapper), "policy": bool(args.policy)}
+
+
 def alg_bytes(lay):
     """both obs written (52 hw) + interior of maze_map r/w (6 hw) + dynamic fields r/w (82)
     + key/actions in, reward/shaped/dones out (35)."""
@@ -185,7 +193,7 @@ def reference_line(args, lay, value, steps, warmup, ms_per_step, n_envs, cores, 
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(args, lay), "sample_envs_per_step": n_envs},
+            "config": workload_config(args, lay, max(1, args.gpus)), "run": {"sample_envs_per_step": n_envs},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -771,8 +779,8 @@ def run_ours(args):
             "requested_steps": args.steps, "replays": K // BLOCK, "timed_window_ms": ms,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, lay), "envs_per_gpu": N, "global_envs": n_global,
-                       "l2": (f"inputs larger than L2: {R} independent env batches + {OBS_SLOTS} observation slots "
+            "config": workload_config(args, lay, world),
+            "run": {"l2": (f"inputs larger than L2: {R} independent env batches + {OBS_SLOTS} observation slots "
                               f"round-robin (state {R * N * (env.info.map_bytes_per_env + 41) / 1e6:.0f} MB + obs "
                               f"{OBS_SLOTS * 2 * N * h * w * 26 / 1e6:.0f} MB per cycle vs 126 MB L2)") if not RO else
                              (f"outputs larger than L2: every launch writes a fresh uint8[{RO}, 2, N, h, w, 26] trajectory buffer "
@@ -803,10 +811,10 @@ def run_ours(args):
                                 "warp_instructions_per_row": WI_ROW, "rows_per_launch": 2 * N, "avg_launch_us": policy_us,
                                 "note": "issue-slot bound: 148 SMs x 4 schedulers x SM clock; DRAM < 1 % and tensor pipe < 10 % busy "
                                         "for this kernel (profiles/r01_ncu_policy_kernel.txt)"}
-        line["config"]["actions"] = ("sampled on the device from the actor-critic MLP (architectures/mlp.py, random orthogonal "
+        line["run"]["actions"] = ("sampled on the device from the actor-critic MLP (architectures/mlp.py, random orthogonal "
                                      "init, fp16 tensor-core layer 2) evaluated on the previous step's observations")
-        line["config"]["policy_rows_per_step"] = 2 * N
-        line["config"]["policy_input"] = args.policy_input
+        line["run"]["policy_rows_per_step"] = 2 * N
+        line["run"]["policy_input"] = args.policy_input
     if stats is not None:
         line["stats"] = stats.cpu().tolist()
     if stats_win is not None:
