@@ -47,7 +47,10 @@ class PolicyRollout:
         done     bool [T, N]      (== dones["__all__"] == each agent's done)
     """
 
-    def __init__(self, env, network, params, state, rng, num_steps, *, log=None, stats=None, graph=True):
+    def __init__(self, env, network, params, state, rng, num_steps, *, log=None, stats=None, graph=True, shard=None):
+        """`shard=(first, n_global)`: `state` holds envs [first, first + N) of a global batch of n_global environments (one GPU's
+        slice of the env axis); per-env keys and the categorical draws are then exactly those of the single-device rollout over
+        the whole batch (`split(key, n_global)[first + i]`, `oc_policy_set_shard`)."""
         from . import random as jr
         self.env, self.net, self.params, self.state = env, network, params, state
         self.T, self.N = int(num_steps), int(state.time.shape[0])
@@ -65,7 +68,8 @@ class PolicyRollout:
         self.subkeys = torch.empty((2 * T, 2), dtype=torch.uint32, device=dev)
         self._log, self._stats = log, stats
         self._jr = jr
-        network.bind(params, env=env)
+        self._first, self._n_global = (int(shard[0]), int(shard[1])) if shard is not None else (0, self.N)
+        network.bind(params, env=env, shard=shard)
         first = env.get_obs(state, cells=self.cells)
         self.obs[0, 0].copy_(first["agent_0"])
         self.obs[0, 1].copy_(first["agent_1"])
@@ -90,7 +94,7 @@ class PolicyRollout:
             net.act_cells(self.params, self.cells, self.subkeys[2 * t], out=out)
             step_out = {"obs0": self.obs[t + 1, 0], "obs1": self.obs[t + 1, 1], "reward": self.reward[t],
                         "shaped0": self.shaped[t, 0], "shaped1": self.shaped[t, 1], "done": self.done[t], "cells": self.cells}
-            key = jr.LazySplit(self.subkeys[2 * t + 1], N)                  # split(_rng, num_envs), derived in the kernel
+            key = jr.LazySplit(self.subkeys[2 * t + 1], self._n_global, self._first, N)   # split(_rng, num_envs), derived in the kernel
             acts = {"agent_0": self.action[t, :N], "agent_1": self.action[t, N:]}
             env.step(key, self.state, acts, donate=True, out=step_out, log=self._log, stats=self._stats)
 

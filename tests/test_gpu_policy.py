@@ -480,3 +480,34 @@ def test_sharded_draws_equal_the_single_device_draws():
     a, _, _ = net.act_cells(Ps, cells[300:633].contiguous(), key)
     rows = torch.cat([torch.arange(300, 633), N + torch.arange(300, 633)]).cuda()
     assert not torch.equal(a, a_f[rows])
+
+
+def test_policy_rollout_shards_reproduce_the_single_device_rollout():
+    """Two PolicyRollouts over the two halves of the env axis (shard=...) produce, concatenated, exactly the trajectory of one
+    PolicyRollout over the whole batch: same keys, same categorical draws, same environments."""
+    from jaxovercooked_b200.rollout import PolicyRollout
+    N, T = 256, 12
+    env = ocb.make("overcooked", layout=ocb.overcooked_layouts["cramped_room"], random_reset=True, max_steps=7)
+    params = po.make_params(5, env.height * env.width * 26)
+    params["params"]["Dense_2"]["kernel"] = params["params"]["Dense_2"]["kernel"] * 50.0
+    keys = jr.split(jr.PRNGKey(3), N)
+    rng = jr.PRNGKey(9)
+
+    def run(lo, hi, shard):
+        net = ActorCritic(6)
+        P = net.params_from_numpy(params)
+        _, st = env.reset(keys[lo:hi].contiguous())
+        ro = PolicyRollout(env, net, P, st, rng, T, graph=False, shard=shard)
+        ro.run()
+        torch.cuda.synchronize()
+        return ro
+
+    full = run(0, N, None)
+    a, b = run(0, N // 2, (0, N)), run(N // 2, N, (N // 2, N))
+    h = N // 2
+    for t in range(T):
+        act = full.action[t].view(2, N)
+        assert torch.equal(torch.cat([a.action[t].view(2, h), b.action[t].view(2, h)], 1), act), f"actions t={t}"
+        assert torch.equal(torch.cat([a.reward[t], b.reward[t]]), full.reward[t]) and torch.equal(torch.cat([a.done[t], b.done[t]]), full.done[t])
+        assert torch.equal(torch.cat([a.obs[t + 1, 0], b.obs[t + 1, 0]]), full.obs[t + 1, 0]), f"obs t={t}"
+    assert int(full.done.sum()) > 0 and len(torch.unique(full.action)) == 6

@@ -347,3 +347,52 @@ def test_rollout_matches_reference_golden(case):
         for f in LOG_FIELDS:
             assert_same(getattr(st, f).cpu().numpy(), g["lw_" + f][T - 1], f"final log {f}")
         assert_same(info["returned_episode"].cpu().numpy(), g["lw_returned_episode"], "returned_episode")
+
+
+@pytest.mark.parametrize("which", ["configs2_padded_cl", "configs4_10x10_random_reset"])
+def test_rollout_baseline_config_sizes(which):
+    """BASELINE.json configs[2] (one GPU's share: a padded 5x9 CL layout, 32,768 envs, LogWrapper + statistics) and configs[4]
+    (10x10 padded layout, random_reset, 65,536 envs) through oc_rollout: bit-identical to the one-launch-per-step path at full
+    size, and a 512-env prefix against the oracle."""
+    ocb, ocr, orc, gh = _mods()
+    from jaxovercooked_b200.layouts import cl_sequence_padded
+    if which == "configs2_padded_cl":
+        lay, N, T, rr, log = cl_sequence_padded()["counter_circuit"], 32768, 24, False, True
+    else:
+        lay, N, T, rr, log = ocb.overcooked_layouts["easy_layout_padded"], 65536, 12, True, False
+    max_steps = 9
+    env = ocb.make("overcooked", layout=lay, random_reset=rr, max_steps=max_steps)
+    k0 = ocr.split(ocr.PRNGKey(0), N)
+    _, st = env.reset(k0)
+    off = torch.randint(0, max_steps, (N,), dtype=torch.int32, device="cuda")
+    st.time.copy_(off)
+    st_b = st.clone()
+    keys = ocr.split_chain(ocr.PRNGKey(1), T)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = {a: torch.randint(0, 6, (T, N), dtype=torch.int32, device="cuda", generator=g) for a in ("agent_0", "agent_1")}
+    mk_log = lambda: {f: torch.zeros((N, 2), dtype=torch.float32, device="cuda") for f in LOG_FIELDS}
+    log_a, log_b = (mk_log(), mk_log()) if log else (None, None)
+    stats_a = torch.zeros(8, dtype=torch.int64, device="cuda") if log else None
+    stats_b = torch.zeros(8, dtype=torch.int64, device="cuda") if log else None
+    obs, _, rew, done, info = env.rollout(keys, st, acts, log=log_a, stats=stats_a)
+    # oracle on a prefix (same per-env keys: split(keys[t], N)[:P])
+    P = 512
+    ref = orc.Oracle(lay, random_reset=rr, max_steps=max_steps)
+    _, rst = ref.reset(k0[:P].cpu().numpy())
+    rst["time"][:] = off[:P].cpu().numpy()
+    for t in range(T):
+        at = {"agent_0": acts["agent_0"][t], "agent_1": acts["agent_1"][t]}
+        ob, st_b, rw, dn, inf = env.step(ocr.LazySplit(keys[t], N), st_b, at, donate=True, log=log_b, stats=stats_b)
+        assert torch.equal(ob["agent_0"], obs["agent_0"][t]) and torch.equal(ob["agent_1"], obs["agent_1"][t]), f"t={t}"
+        assert torch.equal(rw["agent_0"], rew["agent_0"][t]) and torch.equal(dn["__all__"], done["__all__"][t])
+        kt = ocr.split(keys[t], N, count=P).cpu().numpy()
+        (r0, r1), rr_, s0, s1, dd = ref.step(kt, rst, acts["agent_0"][t, :P].cpu().numpy(), acts["agent_1"][t, :P].cpu().numpy())
+        assert_same(obs["agent_0"][t, :P].cpu().numpy(), r0, f"t={t} obs0 vs oracle")
+        assert_same(obs["agent_1"][t, :P].cpu().numpy(), r1, f"t={t} obs1 vs oracle")
+    for f in ("agent_pos", "agent_dir_idx", "agent_inv", "maze_map", "time"):
+        assert torch.equal(getattr(st, f), getattr(st_b, f)), f
+    if log:
+        for f in LOG_FIELDS:
+            assert torch.equal(log_a[f], log_b[f]), f
+        assert torch.equal(stats_a, stats_b) and int(stats_a[6]) == N * T
+    assert int(done["__all__"].sum()) > 0
