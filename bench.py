@@ -9,10 +9,15 @@ A "step" is one pass of the hot path (split key -> step_env -> auto-reset -> bot
 of `--envs` environments per GPU with synthetic uniform-random actions.  Workload = BASELINE.json configs[1]:
 cramped_room, 65,536 envs per GPU.  One JSON line is printed by rank 0.
 
-Timing hygiene: W >= 3 warm-up steps; `--rotate` independent env batches (state) and 8 observation slots are
-used round-robin so consecutive steps never touch the same lines and the per-cycle working set exceeds the
-126 MB L2; the timed region is a replayed CUDA graph (one kernel launch per step) bracketed by barrier +
-synchronize, timed with CUDA events on the launching stream, max over ranks.
+By default the steps run through `oc_rollout`, `--rollout-steps` (128 = the reference's scan length, baselines/IPPO_CL.py:42,577)
+steps per launch with the environments resident on chip -- what the reference's `lax.scan` over `vmap(env.step)` does when the
+actions are given; `--rollout-steps 0` launches one `oc_step` kernel per step (what a policy in the loop needs).
+
+Timing hygiene: W >= 3 warm-up steps; `--rotate` independent env batches (state) are stepped round-robin and every launch
+writes a fresh trajectory buffer far larger than the 126 MB L2 (one-launch-per-step mode: 8 observation slots round-robin);
+the timed region is a replayed CUDA graph bracketed by barrier + synchronize, timed with CUDA events on the launching stream,
+max over ranks, and never shorter than `--min-ms` (250 ms) whatever `--steps` says; the i.i.d. actions and the per-step subkeys
+are re-drawn on the device inside the timed region.
 """
 import argparse
 import json
